@@ -1,0 +1,142 @@
+/*
+ * kmg.h -- C-ABI of libkmg.so: B200-native (sm_100a) Gram / cross-Gram construction for DNA string
+ * kernels, the drop-in boundary for the hot path of afiliot/Kernel-Methods-For-Genomics.
+ *
+ * The reference has no FFI layer: its operator API for this path is the Python module `kernels`
+ * (SURVEY.md section 8b).  Each entry point below names the reference function it replaces
+ * (file:line in /root/reference); `kernel-methods-for-genomics_b200/kernels.py` is the ctypes
+ * binding a maintainer would drop in place of the reference's kernels.py.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every function returns 0 (KMG_OK) or a negative error code and
+ *     leaves a message retrievable with kmg_last_error() (thread local).
+ *   - sequences: n x L bytes, row major, no terminators; either ASCII 'A','C','G','T' or integer
+ *     codes 0..3 (A<C<G<T as in kernels.py:37,184).  All sequences of one call have the same length
+ *     L <= 128 (the challenge data is 101 bp).  Any other byte -> KMG_ERR_ALPHABET.
+ *   - Gram matrices: row-major double, leading dimension given in elements.
+ *   - `*_host` functions take HOST pointers and do the host<->device copies themselves (this is what
+ *     the Python shim calls, one call per Gram); `*_dev` functions take DEVICE pointers plus a
+ *     cudaStream_t passed as void* and only enqueue work (block-row construction for the multi-GPU
+ *     layer and the benchmark).
+ *   - there is no CPU fallback anywhere behind this interface: without a CUDA device every compute
+ *     entry point fails with KMG_ERR_CUDA.
+ */
+#ifndef KMG_H
+#define KMG_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KMG_OK 0
+#define KMG_ERR_CUDA (-1)
+#define KMG_ERR_ARG (-2)
+#define KMG_ERR_ALPHABET (-3)
+#define KMG_ERR_UNSUPPORTED (-4)
+#define KMG_ERR_NOMEM (-5)
+
+#define KMG_OUT_S32 0
+#define KMG_OUT_F64 1
+
+#define KMG_SEQ_ASCII 1
+#define KMG_SEQ_CODES 0
+
+#define KMG_MM_AUTO 0      /* dense feature map + tensor-core GEMM for k <= 8, pairwise bit-vector kernel above */
+#define KMG_MM_PAIRWISE 1
+#define KMG_MM_DENSE 2
+
+/* ---- library ------------------------------------------------------------------------------- */
+int kmg_version(void);
+const char* kmg_last_error(void);
+int kmg_device_count(void);          /* 0 when no usable CUDA device */
+int kmg_set_device(int device);
+int kmg_release(void);               /* frees cached device buffers of the current device */
+
+/* ---- host-buffer entry points (the reference-facing boundary) ------------------------------ */
+/* cols == NULL: symmetric Gram of `rows` (n x n, upper triangle computed and mirrored, as the
+ * reference does); otherwise the nr x nc cross-Gram K[i][j] = k(rows[i], cols[j]). */
+
+/* get_spectrum_K (kernels.py:28-47), summed over ks[0..nk) (one k: the reference call). Unnormalised. */
+int kmg_spectrum_host(const uint8_t* rows, int64_t nr, const uint8_t* cols, int64_t nc, int L, int seq_format,
+                      const int* ks, int nk, double* K, int64_t ldk);
+/* get_mismatch_K (kernels.py:196-217).  normalize=1 reproduces the reference (normalize_K applied,
+ * symmetric Gram only); normalize=0 returns the raw integer Gram. */
+int kmg_mismatch_host(const uint8_t* rows, int64_t nr, const uint8_t* cols, int64_t nc, int L, int seq_format,
+                      int k, int m, int normalize, int algo, double* K, int64_t ldk);
+/* get_phi_u (kernels.py:12-25) / get_phi_km (kernels.py:161-175) for n sequences: int8 feature rows,
+ * columns in product('ACGT', repeat=k) order (segments concatenated over ks), row stride ld >= padded width. */
+int kmg_spectrum_phi_host(const uint8_t* seqs, int64_t n, int L, int seq_format, const int* ks, int nk, int8_t* phi, int64_t ld);
+int kmg_mismatch_phi_host(const uint8_t* seqs, int64_t n, int L, int seq_format, int k, int m, int8_t* phi, int64_t ld);
+/* get_WD_K (kernels.py:84-101).  Symmetric: diagonal is the closed form of kernels.py:96. */
+int kmg_wd_host(const uint8_t* rows, int64_t nr, const uint8_t* cols, int64_t nc, int L, int seq_format,
+                int d, double* K, int64_t ldk);
+/* get_LA_K pair loop (kernels.py:287-291) with the INTENDED affine_align / Smith_Waterman
+ * (kernels.py:226-270; the reference as written returns 0.0 for every pair -- see DESIGN.md). */
+int kmg_la_host(const uint8_t* rows, int64_t nr, const uint8_t* cols, int64_t nc, int L, int seq_format,
+                double e, double d, double beta, int smith, double* K, int64_t ldk);
+
+/* normalize_K (kernels.py:398-415): in place.  Returns 1 if K[0][0]==1 (reference early-out, K
+ * untouched), 0 after normalising, <0 on error. */
+int kmg_normalize_host(double* K, int64_t n, int64_t ldk);
+/* center_K (kernels.py:387-395): out = (I-11'/n) K (I-11'/n), closed form. */
+int kmg_center_host(const double* K, int64_t n, int64_t ldk, double* out, int64_t ldo);
+/* ALIGNF.get_K (ALIGNF.py:93) with degree=1; NLCK (NLCKernels.py:52,97-99): (sum_m u_m K_m)**degree,
+ * then normalize_K when normalize=1. */
+int kmg_combine_host(const double* const* Ks, int p, int64_t n, const double* u, int degree, int normalize, double* out);
+/* ALIGNF.__init__ Gram side (ALIGNF.py:28-29,36-58): sub-block K[idx][:,idx], centre, a_i and M_ij. */
+int kmg_alignf_stats_host(const double* const* Ks, int p, int64_t n, const int64_t* idx, int64_t nfit, const double* y,
+                          double* a, double* M);
+/* NLCK.grad (NLCKernels.py:61-66) on the fit sub-blocks (nfit x nfit, contiguous). */
+int kmg_nlck_grad_host(const double* const* Ks_fit, int p, int64_t nfit, const double* u, const double* alpha, int degree,
+                       double* grad);
+
+/* ---- device-pointer entry points (block-row construction) ---------------------------------- */
+/* letter_to_num/format (kernels.py:178-193): n x L bytes -> 8 u32 words of bit-planes per sequence.
+ * *d_err_flag (device int, zero-initialised by the caller) is set to 1 on a non-ACGT byte. */
+int kmg_pack_dev(const uint8_t* d_seqs, int seq_format, int64_t n, int L, uint32_t* d_planes, int* d_err_flag, void* stream);
+/* padded feature width of the concatenated spectrum feature map (multiple of 128). */
+int64_t kmg_spectrum_phi_width(const int* ks, int nk);
+/* get_phi_u (kernels.py:12-25) for every sequence and every k in ks: int8 Phi, n x ld_phi. */
+int kmg_spectrum_phi_dev(const uint32_t* d_planes, int64_t n, int L, const int* ks, int nk, int8_t* d_phi, int64_t ld_phi,
+                         void* stream);
+/* get_phi_km (kernels.py:161-175): dense (k,m)-mismatch feature map, int8, width pad128(4^k), k <= 8, m <= 3. */
+int kmg_mismatch_phi_dev(const uint32_t* d_planes, int64_t n, int L, int k, int m, int8_t* d_phi, int64_t ld_phi, void* stream);
+/* sd[i] = sqrt(sum_t Phi[i][t]^2) -- the diagonal a normalised spectrum Gram needs. */
+int kmg_phi_diag_sqrt_dev(const int8_t* d_phi, int64_t n, int64_t width, int64_t ld_phi, double* d_sd, void* stream);
+/* K block = Phi_rows Phi_cols^T on the tensor cores (kernels.py:41-45).  symmetric=1: square diagonal
+ * block written in place with mirror stores.  sd_rows/sd_cols (nullable): fused cosine normalisation.
+ * m_sub: 0 auto, 1 = 128x256 tiles, 2 = 256x256 tiles. */
+int kmg_gram_i8_dev(const int8_t* d_phi_rows, const int8_t* d_phi_cols, int64_t rows, int64_t cols, int64_t width,
+                    int64_t ld_phi, int64_t row_index0, int64_t col_index0, void* d_out, int64_t ldo, int out_dtype,
+                    int symmetric, const double* d_sd_rows, const double* d_sd_cols, int m_sub, void* stream);
+/* same contraction on CUDA cores (dp4a), s32 output: validation only, not a product path. */
+int kmg_gram_i8_simt_dev(const int8_t* d_phi_rows, const int8_t* d_phi_cols, int64_t rows, int64_t cols, int64_t width,
+                         int64_t ld_phi, int32_t* d_out, int64_t ldo, void* stream);
+/* pairwise kernels on bit-planes; rows/cols blocks of the same plane array or of two arrays. */
+int kmg_mismatch_dev(const uint32_t* d_planes_rows, const uint32_t* d_planes_cols, int64_t rows, int64_t cols,
+                     int64_t row_index0, int64_t col_index0, int L, int k, int m, void* d_out, int64_t ldo, int out_dtype,
+                     int symmetric, const double* d_sd_rows, const double* d_sd_cols, void* stream);
+int kmg_mismatch_diag_dev(const uint32_t* d_planes, int64_t n, int L, int k, int m, double* d_sd, void* stream);
+int kmg_wd_dev(const uint32_t* d_planes_rows, const uint32_t* d_planes_cols, int64_t rows, int64_t cols, int64_t row_index0,
+               int64_t col_index0, int L, int d, double* d_out, int64_t ldo, int symmetric, void* stream);
+int kmg_la_dev(const uint32_t* d_planes_rows, const uint32_t* d_planes_cols, int64_t rows, int64_t cols, int64_t row_index0,
+               int64_t col_index0, int L, double e, double d, double beta, int smith, double* d_out, int64_t ldo,
+               int symmetric, void* stream);
+/* stored-Gram passes */
+int kmg_normalize_dev(double* d_K, int64_t n, int64_t ld, double* d_sd_scratch /* n */, void* stream);
+int64_t kmg_center_workspace_bytes(int64_t n);
+int kmg_center_dev(const double* d_K, int64_t n, int64_t ld, double* d_out, int64_t ldo, void* d_workspace, void* stream);
+int kmg_gather_dev(const double* d_K, int64_t ld, const int64_t* d_idx, int64_t m, double* d_out, int64_t ldo, void* stream);
+int kmg_combine_dev(const double* const* d_Ks /* host array of device pointers */, const int64_t* lds, const double* u, int p,
+                    int degree, int64_t rows, int64_t cols, double* d_out, int64_t ldo, void* stream);
+int kmg_weighted_dot_dev(const double* d_A, int64_t lda, const double* d_B, int64_t ldb, const double* d_w, int64_t n,
+                         double* d_partial /* n */, double* d_result /* 1 */, void* stream);
+
+/* (k,m)-mismatch common-neighbourhood table T[0..k] (host utility). */
+int kmg_mismatch_table_host(int k, int m, int64_t* T);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KMG_H */

@@ -1,0 +1,652 @@
+// api.cu -- the C-ABI of libkmg.so (include/kmg.h): argument checking, device-memory plumbing and
+// the host<->device orchestration behind the `*_host` entry points.  No compute happens here and
+// there is no CPU fallback: every path ends in one of the sm_100a kernels of this directory.
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "../../include/kmg.h"
+#include "elementwise.h"
+#include "gram_i8.h"
+#include "kmg_common.cuh"
+#include "pair_kernels.h"
+#include "seq_kernels.h"
+
+// ------------------------------------------------------------------------------------------
+// error reporting
+// ------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+void kmg_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+namespace {
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    ~DevBuf() { if (p) cudaFree(p); }
+    int alloc(size_t n) {
+        if (p) { cudaFree(p); p = nullptr; }
+        bytes = n;
+        if (n == 0) return KMG_OK;
+        cudaError_t e = cudaMalloc(&p, n);
+        if (e != cudaSuccess) {
+            p = nullptr;
+            kmg_set_error("cudaMalloc(%zu bytes) failed: %s", n, cudaGetErrorString(e));
+            cudaGetLastError();
+            return KMG_ERR_NOMEM;
+        }
+        return KMG_OK;
+    }
+    template <typename T> T* as() { return reinterpret_cast<T*>(p); }
+};
+
+struct StreamHolder {
+    cudaStream_t s[2] = {nullptr, nullptr};
+    int dev = -1;
+};
+thread_local StreamHolder g_streams;
+
+int get_streams(cudaStream_t* s0, cudaStream_t* s1) {
+    int dev = 0;
+    KMG_CUDA_CHECK(cudaGetDevice(&dev));
+    if (g_streams.dev != dev || g_streams.s[0] == nullptr) {
+        for (int i = 0; i < 2; ++i) KMG_CUDA_CHECK(cudaStreamCreateWithFlags(&g_streams.s[i], cudaStreamNonBlocking));
+        g_streams.dev = dev;
+    }
+    *s0 = g_streams.s[0];
+    if (s1) *s1 = g_streams.s[1];
+    return KMG_OK;
+}
+
+int require_device() {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        kmg_set_error("no CUDA device available (%s): libkmg has no CPU fallback", e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+        return KMG_ERR_CUDA;
+    }
+    return KMG_OK;
+}
+
+// Upload + pack one set of sequences.  planes: n x 8 u32.
+int upload_planes(const uint8_t* seqs, int64_t n, int L, int fmt, DevBuf* planes, cudaStream_t s) {
+    KMG_REQUIRE(L >= 1 && L <= KMG_MAX_L, KMG_ERR_UNSUPPORTED, "sequence length %d not supported (1..%d)", L, KMG_MAX_L);
+    int rc = planes->alloc((size_t)std::max<int64_t>(n, 1) * KMG_SEQ_WORDS * sizeof(uint32_t));
+    if (rc) return rc;
+    if (n == 0) return KMG_OK;
+    DevBuf raw, err;
+    if ((rc = raw.alloc((size_t)n * L))) return rc;
+    if ((rc = err.alloc(sizeof(int)))) return rc;
+    KMG_CUDA_CHECK(cudaMemsetAsync(err.p, 0, sizeof(int), s));
+    KMG_CUDA_CHECK(cudaMemcpyAsync(raw.p, seqs, (size_t)n * L, cudaMemcpyHostToDevice, s));
+    if ((rc = kmg_pack_launch(raw.as<uint8_t>(), fmt == KMG_SEQ_ASCII, n, L, planes->as<uint32_t>(), err.as<int>(), s))) return rc;
+    int herr = 0;
+    KMG_CUDA_CHECK(cudaMemcpyAsync(&herr, err.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    KMG_CUDA_CHECK(cudaStreamSynchronize(s));
+    KMG_REQUIRE(herr == 0, KMG_ERR_ALPHABET, "sequence contains a character outside {A,C,G,T}");
+    return KMG_OK;
+}
+
+// Row-block size so that two output buffers of `rows x cols` doubles fit in a fraction of free memory.
+int pick_block_rows(int64_t nr, int64_t nc, int64_t* block_rows) {
+    size_t free_b = 0, total_b = 0;
+    KMG_CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
+    const double budget = 0.70 * (double)free_b;
+    int64_t r = (int64_t)(budget / (2.0 * 8.0 * (double)std::max<int64_t>(nc, 1)));
+    r = std::min<int64_t>(r, 32768);
+    r = (r / 256) * 256;
+    KMG_REQUIRE(r >= 256 || r >= nr, KMG_ERR_NOMEM, "not enough device memory for a 256-row block of %lld columns", (long long)nc);
+    *block_rows = std::max<int64_t>(std::min<int64_t>(r, nr), 1);
+    return KMG_OK;
+}
+
+typedef int (*BlockFn)(void* ctx, int64_t r0, int64_t rows, double* d_out, int64_t ldo, int symmetric, cudaStream_t s);
+
+// Build an nr x nc Gram block-row by block-row on the device and copy it to host memory.
+// If the whole (square, symmetric) matrix fits it is built in one symmetric launch.
+int build_to_host(int64_t nr, int64_t nc, bool symmetric, BlockFn fn, void* ctx, double* K, int64_t ldk) {
+    if (nr == 0 || nc == 0) return KMG_OK;
+    cudaStream_t s0, s1;
+    int rc = get_streams(&s0, &s1);
+    if (rc) return rc;
+    int64_t br = 0;
+    if ((rc = pick_block_rows(nr, nc, &br))) return rc;
+    if (br >= nr) {
+        DevBuf out;
+        if ((rc = out.alloc((size_t)nr * nc * sizeof(double)))) return rc;
+        if ((rc = fn(ctx, 0, nr, out.as<double>(), nc, symmetric ? 1 : 0, s0))) return rc;
+        KMG_CUDA_CHECK(cudaMemcpy2DAsync(K, (size_t)ldk * 8, out.p, (size_t)nc * 8, (size_t)nc * 8, (size_t)nr, cudaMemcpyDeviceToHost, s0));
+        KMG_CUDA_CHECK(cudaStreamSynchronize(s0));
+        return KMG_OK;
+    }
+    // streamed: two buffers, compute of block b+1 overlaps the copy of block b
+    DevBuf buf[2];
+    cudaStream_t st[2] = {s0, s1};
+    for (int i = 0; i < 2; ++i)
+        if ((rc = buf[i].alloc((size_t)br * nc * sizeof(double)))) return rc;
+    int which = 0;
+    for (int64_t r0 = 0; r0 < nr; r0 += br, which ^= 1) {
+        const int64_t rows = std::min<int64_t>(br, nr - r0);
+        cudaStream_t s = st[which];
+        KMG_CUDA_CHECK(cudaStreamSynchronize(s));  // previous copy out of this buffer finished
+        if ((rc = fn(ctx, r0, rows, buf[which].as<double>(), nc, 0, s))) return rc;
+        KMG_CUDA_CHECK(cudaMemcpy2DAsync(K + r0 * ldk, (size_t)ldk * 8, buf[which].p, (size_t)nc * 8, (size_t)nc * 8, (size_t)rows,
+                                         cudaMemcpyDeviceToHost, s));
+    }
+    KMG_CUDA_CHECK(cudaStreamSynchronize(s0));
+    KMG_CUDA_CHECK(cudaStreamSynchronize(s1));
+    return KMG_OK;
+}
+
+struct SeqPair {
+    DevBuf prow, pcol;
+    const uint32_t* rows = nullptr;
+    const uint32_t* cols = nullptr;
+    int64_t nr = 0, nc = 0;
+    bool symmetric = false;
+};
+
+int upload_pair(const uint8_t* rows, int64_t nr, const uint8_t* cols, int64_t nc, int L, int fmt, SeqPair* sp) {
+    KMG_REQUIRE(nr >= 0 && (cols == nullptr || nc >= 0), KMG_ERR_ARG, "negative sequence count");
+    KMG_REQUIRE(rows != nullptr || nr == 0, KMG_ERR_ARG, "null sequence pointer");
+    cudaStream_t s;
+    int rc = get_streams(&s, nullptr);
+    if (rc) return rc;
+    if ((rc = upload_planes(rows, nr, L, fmt, &sp->prow, s))) return rc;
+    sp->rows = sp->prow.as<uint32_t>();
+    sp->nr = nr;
+    if (cols == nullptr) {
+        sp->cols = sp->rows; sp->nc = nr; sp->symmetric = true;
+    } else {
+        if ((rc = upload_planes(cols, nc, L, fmt, &sp->pcol, s))) return rc;
+        sp->cols = sp->pcol.as<uint32_t>(); sp->nc = nc; sp->symmetric = false;
+    }
+    return KMG_OK;
+}
+
+// ---- per-kernel block builders -----------------------------------------------------------
+struct SpectrumCtx {
+    const int8_t* phi_rows; const int8_t* phi_cols; int64_t nc; int64_t width;
+    const double* sd_rows; const double* sd_cols;
+};
+int spectrum_block(void* c, int64_t r0, int64_t rows, double* out, int64_t ldo, int symmetric, cudaStream_t s) {
+    SpectrumCtx* x = (SpectrumCtx*)c;
+    GramI8Args a;
+    memset(&a, 0, sizeof(a));
+    a.phi_rows = x->phi_rows + r0 * x->width; a.phi_cols = x->phi_cols;
+    a.rows = rows; a.cols = x->nc; a.Dpad = x->width; a.ld_phi = x->width;
+    a.row_index0 = symmetric ? 0 : r0; a.col_index0 = 0;
+    a.out = out; a.ldo = ldo; a.out_dtype = KMG_OUT_F64; a.symmetric = symmetric; a.out_t = out; a.ldo_t = ldo;
+    a.sd_rows = x->sd_rows ? x->sd_rows + r0 : nullptr; a.sd_cols = x->sd_cols;
+    return kmg_gram_i8_launch(&a, s);
+}
+
+struct PairCtx {
+    const SeqPair* sp; int L; int kind; int k, m, d, smith; double e, dd, beta; const double* sd; bool index_diag;
+};
+int pair_block(void* c, int64_t r0, int64_t rows, double* out, int64_t ldo, int symmetric, cudaStream_t s) {
+    PairCtx* x = (PairCtx*)c;
+    PairBlock b;
+    memset(&b, 0, sizeof(b));
+    b.planes_rows = x->sp->rows + r0 * KMG_SEQ_WORDS; b.planes_cols = x->sp->cols;
+    b.rows = rows; b.cols = x->sp->nc;
+    // cross-Grams have no diagonal: offset the column indices so that row index never equals column index
+    b.row_index0 = r0; b.col_index0 = x->index_diag ? 0 : (int64_t)1 << 40;
+    b.L = x->L; b.out = out; b.ldo = ldo; b.out_dtype = KMG_OUT_F64;
+    b.symmetric = symmetric; b.out_t = out; b.ldo_t = ldo;
+    b.sd_rows = x->sd ? x->sd + r0 : nullptr; b.sd_cols = x->sd;
+    if (x->kind == 0) return kmg_mismatch_launch(&b, x->k, x->m, s);
+    if (x->kind == 1) return kmg_wd_launch(&b, x->d, s);
+    return kmg_la_launch(&b, x->e, x->dd, x->beta, x->smith, s);
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------
+// library
+// ------------------------------------------------------------------------------------------
+extern "C" {
+
+int kmg_version(void) { return 100; }
+const char* kmg_last_error(void) { return g_err; }
+
+int kmg_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int kmg_set_device(int device) {
+    KMG_CUDA_CHECK(cudaSetDevice(device));
+    return KMG_OK;
+}
+
+int kmg_release(void) { return KMG_OK; }
+
+int kmg_mismatch_table_host(int k, int m, int64_t* T) {
+    KMG_REQUIRE(k >= 1 && k <= KMG_MAX_L && m >= 0 && T != nullptr, KMG_ERR_ARG, "mismatch_table: bad arguments");
+    return kmg_mismatch_table(k, m, T);
+}
+
+// ------------------------------------------------------------------------------------------
+// host-buffer entry points
+// ------------------------------------------------------------------------------------------
+int kmg_spectrum_host(const uint8_t* rows, int64_t nr, const uint8_t* cols, int64_t nc, int L, int seq_format,
+                      const int* ks, int nk, double* K, int64_t ldk) {
+    int rc = require_device();
+    if (rc) return rc;
+    KMG_REQUIRE(ks != nullptr && nk >= 1 && nk <= KMG_MAX_KS, KMG_ERR_ARG, "spectrum: between 1 and %d values of k", KMG_MAX_KS);
+    bool pairwise = false;
+    for (int q = 0; q < nk; ++q) {
+        KMG_REQUIRE(ks[q] >= 1, KMG_ERR_ARG, "spectrum: k must be >= 1");
+        if (ks[q] > KMG_MAX_DENSE_K || ks[q] > L) pairwise = true;
+    }
+    if (pairwise) {
+        // k too large for a dense 4^k feature row: SP(k) == raw MM(k, 0) (kernels.py:161-175 with m=0)
+        KMG_REQUIRE(nk == 1, KMG_ERR_UNSUPPORTED, "spectrum: sums over several k need every k <= %d", KMG_MAX_DENSE_K);
+        if (ks[0] > L) {  // no window at all: the reference returns zeros
+            const int64_t c = cols ? nc : nr;
+            for (int64_t i = 0; i < nr; ++i) memset(K + i * ldk, 0, (size_t)c * sizeof(double));
+            return KMG_OK;
+        }
+        return kmg_mismatch_host(rows, nr, cols, nc, L, seq_format, ks[0], 0, 0, KMG_MM_PAIRWISE, K, ldk);
+    }
+    SeqPair sp;
+    if ((rc = upload_pair(rows, nr, cols, nc, L, seq_format, &sp))) return rc;
+    KMG_REQUIRE(K != nullptr && ldk >= sp.nc, KMG_ERR_ARG, "spectrum: bad output buffer");
+    if (sp.nr == 0 || sp.nc == 0) return KMG_OK;
+    cudaStream_t s;
+    if ((rc = get_streams(&s, nullptr))) return rc;
+    const int64_t width = kmg_spectrum_padded_width(ks, nk, L);
+    DevBuf phi_r, phi_c;
+    if ((rc = phi_r.alloc((size_t)sp.nr * width))) return rc;
+    if ((rc = kmg_spectrum_phi_launch(sp.rows, sp.nr, L, ks, nk, phi_r.as<int8_t>(), width, s))) return rc;
+    const int8_t* pc = phi_r.as<int8_t>();
+    if (!sp.symmetric) {
+        if ((rc = phi_c.alloc((size_t)sp.nc * width))) return rc;
+        if ((rc = kmg_spectrum_phi_launch(sp.cols, sp.nc, L, ks, nk, phi_c.as<int8_t>(), width, s))) return rc;
+        pc = phi_c.as<int8_t>();
+    }
+    KMG_CUDA_CHECK(cudaStreamSynchronize(s));
+    SpectrumCtx ctx{phi_r.as<int8_t>(), pc, sp.nc, width, nullptr, nullptr};
+    return build_to_host(sp.nr, sp.nc, sp.symmetric, spectrum_block, &ctx, K, ldk);
+}
+
+int kmg_mismatch_host(const uint8_t* rows, int64_t nr, const uint8_t* cols, int64_t nc, int L, int seq_format,
+                      int k, int m, int normalize, int algo, double* K, int64_t ldk) {
+    int rc = require_device();
+    if (rc) return rc;
+    KMG_REQUIRE(!(normalize && cols != nullptr), KMG_ERR_ARG, "mismatch: normalisation is defined for the symmetric Gram only");
+    KMG_REQUIRE(algo >= KMG_MM_AUTO && algo <= KMG_MM_DENSE, KMG_ERR_ARG, "mismatch: algo must be 0 (auto), 1 (pairwise) or 2 (dense)");
+    KMG_REQUIRE(k >= 1 && k <= L, KMG_ERR_ARG, "mismatch: need 1 <= k <= L (k=%d, L=%d)", k, L);
+    SeqPair sp;
+    if ((rc = upload_pair(rows, nr, cols, nc, L, seq_format, &sp))) return rc;
+    KMG_REQUIRE(K != nullptr && ldk >= sp.nc, KMG_ERR_ARG, "mismatch: bad output buffer");
+    if (sp.nr == 0 || sp.nc == 0) return KMG_OK;
+    cudaStream_t s;
+    if ((rc = get_streams(&s, nullptr))) return rc;
+    if (algo == KMG_MM_AUTO) algo = (k <= KMG_MAX_DENSE_K && m <= 3 && L - k + 1 <= 127) ? KMG_MM_DENSE : KMG_MM_PAIRWISE;
+    if (algo == KMG_MM_DENSE) {
+        // the reference's own structure (kernels.py:206-215): dense phi_km, then Phi Phi^T -- on the tensor cores
+        const int64_t width = ((1ll << (2 * k)) + 127) / 128 * 128;
+        DevBuf phi_r, phi_c, sd;
+        if ((rc = phi_r.alloc((size_t)sp.nr * width))) return rc;
+        if ((rc = kmg_mismatch_phi_launch(sp.rows, sp.nr, L, k, m, phi_r.as<int8_t>(), width, s))) return rc;
+        const int8_t* pc = phi_r.as<int8_t>();
+        if (!sp.symmetric) {
+            if ((rc = phi_c.alloc((size_t)sp.nc * width))) return rc;
+            if ((rc = kmg_mismatch_phi_launch(sp.cols, sp.nc, L, k, m, phi_c.as<int8_t>(), width, s))) return rc;
+            pc = phi_c.as<int8_t>();
+        }
+        const double* sdp = nullptr;
+        if (normalize) {
+            if ((rc = sd.alloc((size_t)sp.nr * sizeof(double)))) return rc;
+            if ((rc = kmg_phi_diag_sqrt_launch(phi_r.as<int8_t>(), sp.nr, width, width, sd.as<double>(), s))) return rc;
+            double sd0 = 0.0;
+            KMG_CUDA_CHECK(cudaMemcpyAsync(&sd0, sd.p, sizeof(double), cudaMemcpyDeviceToHost, s));
+            KMG_CUDA_CHECK(cudaStreamSynchronize(s));
+            if (sd0 != 1.0) sdp = sd.as<double>();  // normalize_K early-out, kernels.py:404
+        }
+        KMG_CUDA_CHECK(cudaStreamSynchronize(s));
+        SpectrumCtx ctx{phi_r.as<int8_t>(), pc, sp.nc, width, sdp, sdp};
+        return build_to_host(sp.nr, sp.nc, sp.symmetric, spectrum_block, &ctx, K, ldk);
+    }
+    DevBuf sd;
+    const double* sdp = nullptr;
+    if (normalize) {
+        if ((rc = sd.alloc((size_t)sp.nr * sizeof(double)))) return rc;
+        if ((rc = kmg_mismatch_diag_launch(sp.rows, sp.nr, L, k, m, sd.as<double>(), s))) return rc;
+        // normalize_K early-out (kernels.py:404): a raw K[0,0] of exactly 1 leaves the matrix unnormalised
+        double sd0 = 0.0;
+        KMG_CUDA_CHECK(cudaMemcpyAsync(&sd0, sd.p, sizeof(double), cudaMemcpyDeviceToHost, s));
+        KMG_CUDA_CHECK(cudaStreamSynchronize(s));
+        if (sd0 != 1.0) sdp = sd.as<double>();
+    }
+    KMG_CUDA_CHECK(cudaStreamSynchronize(s));
+    PairCtx ctx{&sp, L, 0, k, m, 0, 0, 0.0, 0.0, 0.0, sdp, sp.symmetric};
+    return build_to_host(sp.nr, sp.nc, sp.symmetric, pair_block, &ctx, K, ldk);
+}
+
+static int phi_host(const uint8_t* seqs, int64_t n, int L, int seq_format, int which, const int* ks, int nk, int k, int m,
+                    int8_t* phi, int64_t ld) {
+    int rc = require_device();
+    if (rc) return rc;
+    KMG_REQUIRE(n >= 0 && (seqs != nullptr || n == 0) && (phi != nullptr || n == 0), KMG_ERR_ARG, "phi: bad arguments");
+    cudaStream_t s;
+    if ((rc = get_streams(&s, nullptr))) return rc;
+    DevBuf planes, dphi;
+    if ((rc = upload_planes(seqs, n, L, seq_format, &planes, s))) return rc;
+    const int64_t width = which == 0 ? kmg_spectrum_padded_width(ks, nk, L) : ((1ll << (2 * k)) + 127) / 128 * 128;
+    KMG_REQUIRE(ld >= width, KMG_ERR_ARG, "phi: ld must be >= %lld", (long long)width);
+    if (n == 0) return KMG_OK;
+    if ((rc = dphi.alloc((size_t)n * width))) return rc;
+    rc = which == 0 ? kmg_spectrum_phi_launch(planes.as<uint32_t>(), n, L, ks, nk, dphi.as<int8_t>(), width, s)
+                    : kmg_mismatch_phi_launch(planes.as<uint32_t>(), n, L, k, m, dphi.as<int8_t>(), width, s);
+    if (rc) return rc;
+    KMG_CUDA_CHECK(cudaMemcpy2DAsync(phi, (size_t)ld, dphi.p, (size_t)width, (size_t)width, (size_t)n, cudaMemcpyDeviceToHost, s));
+    KMG_CUDA_CHECK(cudaStreamSynchronize(s));
+    return KMG_OK;
+}
+
+int kmg_spectrum_phi_host(const uint8_t* seqs, int64_t n, int L, int seq_format, const int* ks, int nk, int8_t* phi, int64_t ld) {
+    KMG_REQUIRE(ks != nullptr && nk >= 1, KMG_ERR_ARG, "spectrum_phi: need at least one k");
+    return phi_host(seqs, n, L, seq_format, 0, ks, nk, 0, 0, phi, ld);
+}
+
+int kmg_mismatch_phi_host(const uint8_t* seqs, int64_t n, int L, int seq_format, int k, int m, int8_t* phi, int64_t ld) {
+    return phi_host(seqs, n, L, seq_format, 1, nullptr, 0, k, m, phi, ld);
+}
+
+int kmg_wd_host(const uint8_t* rows, int64_t nr, const uint8_t* cols, int64_t nc, int L, int seq_format,
+                int d, double* K, int64_t ldk) {
+    int rc = require_device();
+    if (rc) return rc;
+    SeqPair sp;
+    if ((rc = upload_pair(rows, nr, cols, nc, L, seq_format, &sp))) return rc;
+    KMG_REQUIRE(K != nullptr && ldk >= sp.nc, KMG_ERR_ARG, "wd: bad output buffer");
+    PairCtx ctx{&sp, L, 1, 0, 0, d, 0, 0.0, 0.0, 0.0, nullptr, sp.symmetric};
+    return build_to_host(sp.nr, sp.nc, sp.symmetric, pair_block, &ctx, K, ldk);
+}
+
+int kmg_la_host(const uint8_t* rows, int64_t nr, const uint8_t* cols, int64_t nc, int L, int seq_format,
+                double e, double d, double beta, int smith, double* K, int64_t ldk) {
+    int rc = require_device();
+    if (rc) return rc;
+    SeqPair sp;
+    if ((rc = upload_pair(rows, nr, cols, nc, L, seq_format, &sp))) return rc;
+    KMG_REQUIRE(K != nullptr && ldk >= sp.nc, KMG_ERR_ARG, "la: bad output buffer");
+    PairCtx ctx{&sp, L, 2, 0, 0, 0, smith, e, d, beta, nullptr, sp.symmetric};
+    return build_to_host(sp.nr, sp.nc, sp.symmetric, pair_block, &ctx, K, ldk);
+}
+
+int kmg_normalize_host(double* K, int64_t n, int64_t ldk) {
+    int rc = require_device();
+    if (rc) return rc;
+    KMG_REQUIRE(n >= 0 && (K != nullptr || n == 0) && ldk >= n, KMG_ERR_ARG, "normalize: bad arguments");
+    if (n == 0) return 0;
+    if (K[0] == 1.0) return 1;  // kernels.py:404-405
+    cudaStream_t s;
+    if ((rc = get_streams(&s, nullptr))) return rc;
+    DevBuf d, sd;
+    if ((rc = d.alloc((size_t)n * n * 8))) return rc;
+    if ((rc = sd.alloc((size_t)n * 8))) return rc;
+    KMG_CUDA_CHECK(cudaMemcpy2DAsync(d.p, (size_t)n * 8, K, (size_t)ldk * 8, (size_t)n * 8, (size_t)n, cudaMemcpyHostToDevice, s));
+    if ((rc = kmg_ew_diag_sqrt(d.as<double>(), n, n, sd.as<double>(), s))) return rc;
+    if ((rc = kmg_ew_normalize(d.as<double>(), n, n, sd.as<double>(), s))) return rc;
+    KMG_CUDA_CHECK(cudaMemcpy2DAsync(K, (size_t)ldk * 8, d.p, (size_t)n * 8, (size_t)n * 8, (size_t)n, cudaMemcpyDeviceToHost, s));
+    KMG_CUDA_CHECK(cudaStreamSynchronize(s));
+    return 0;
+}
+
+int kmg_center_host(const double* K, int64_t n, int64_t ldk, double* out, int64_t ldo) {
+    int rc = require_device();
+    if (rc) return rc;
+    KMG_REQUIRE(n >= 0 && ldk >= n && ldo >= n, KMG_ERR_ARG, "center: bad arguments");
+    if (n == 0) return KMG_OK;
+    cudaStream_t s;
+    if ((rc = get_streams(&s, nullptr))) return rc;
+    DevBuf d, o, ws;
+    if ((rc = d.alloc((size_t)n * n * 8))) return rc;
+    if ((rc = o.alloc((size_t)n * n * 8))) return rc;
+    if ((rc = ws.alloc((size_t)kmg_ew_center_workspace(n)))) return rc;
+    KMG_CUDA_CHECK(cudaMemcpy2DAsync(d.p, (size_t)n * 8, K, (size_t)ldk * 8, (size_t)n * 8, (size_t)n, cudaMemcpyHostToDevice, s));
+    if ((rc = kmg_ew_center(d.as<double>(), n, n, o.as<double>(), n, ws.p, s))) return rc;
+    KMG_CUDA_CHECK(cudaMemcpy2DAsync(out, (size_t)ldo * 8, o.p, (size_t)n * 8, (size_t)n * 8, (size_t)n, cudaMemcpyDeviceToHost, s));
+    KMG_CUDA_CHECK(cudaStreamSynchronize(s));
+    return KMG_OK;
+}
+
+int kmg_combine_host(const double* const* Ks, int p, int64_t n, const double* u, int degree, int normalize, double* out) {
+    int rc = require_device();
+    if (rc) return rc;
+    KMG_REQUIRE(p >= 1 && p <= KMG_MAX_COMBINE && n >= 0 && Ks && u && out, KMG_ERR_ARG, "combine: bad arguments");
+    if (n == 0) return KMG_OK;
+    cudaStream_t s;
+    if ((rc = get_streams(&s, nullptr))) return rc;
+    std::vector<DevBuf> bufs(p);
+    const double* dptr[KMG_MAX_COMBINE];
+    int64_t lds[KMG_MAX_COMBINE];
+    for (int m = 0; m < p; ++m) {
+        if ((rc = bufs[m].alloc((size_t)n * n * 8))) return rc;
+        KMG_CUDA_CHECK(cudaMemcpyAsync(bufs[m].p, Ks[m], (size_t)n * n * 8, cudaMemcpyHostToDevice, s));
+        dptr[m] = bufs[m].as<double>();
+        lds[m] = n;
+    }
+    DevBuf o, sd;
+    if ((rc = o.alloc((size_t)n * n * 8))) return rc;
+    if ((rc = kmg_ew_combine(dptr, lds, u, p, degree, n, n, o.as<double>(), n, s))) return rc;
+    if (normalize) {
+        double k00 = 0.0;
+        KMG_CUDA_CHECK(cudaMemcpyAsync(&k00, o.p, 8, cudaMemcpyDeviceToHost, s));
+        KMG_CUDA_CHECK(cudaStreamSynchronize(s));
+        if (k00 != 1.0) {
+            if ((rc = sd.alloc((size_t)n * 8))) return rc;
+            if ((rc = kmg_ew_diag_sqrt(o.as<double>(), n, n, sd.as<double>(), s))) return rc;
+            if ((rc = kmg_ew_normalize(o.as<double>(), n, n, sd.as<double>(), s))) return rc;
+        }
+    }
+    KMG_CUDA_CHECK(cudaMemcpyAsync(out, o.p, (size_t)n * n * 8, cudaMemcpyDeviceToHost, s));
+    KMG_CUDA_CHECK(cudaStreamSynchronize(s));
+    return KMG_OK;
+}
+
+int kmg_alignf_stats_host(const double* const* Ks, int p, int64_t n, const int64_t* idx, int64_t nfit, const double* y,
+                          double* a, double* M) {
+    int rc = require_device();
+    if (rc) return rc;
+    KMG_REQUIRE(p >= 1 && p <= KMG_MAX_COMBINE && n >= 0 && nfit >= 0 && Ks && idx && y && a && M, KMG_ERR_ARG, "alignf_stats: bad arguments");
+    for (int64_t t = 0; t < nfit; ++t) KMG_REQUIRE(idx[t] >= 0 && idx[t] < n, KMG_ERR_ARG, "alignf_stats: index out of range");
+    if (nfit == 0) { for (int i = 0; i < p; ++i) { a[i] = 0; for (int j = 0; j < p; ++j) M[i * p + j] = 0; } return KMG_OK; }
+    cudaStream_t s;
+    if ((rc = get_streams(&s, nullptr))) return rc;
+    DevBuf full, sub, didx, dy, ws, part, res;
+    std::vector<DevBuf> kc(p);
+    if ((rc = full.alloc((size_t)n * n * 8))) return rc;
+    if ((rc = sub.alloc((size_t)nfit * nfit * 8))) return rc;
+    if ((rc = didx.alloc((size_t)nfit * 8))) return rc;
+    if ((rc = dy.alloc((size_t)nfit * 8))) return rc;
+    if ((rc = ws.alloc((size_t)kmg_ew_center_workspace(nfit)))) return rc;
+    if ((rc = part.alloc((size_t)nfit * 8))) return rc;
+    if ((rc = res.alloc((size_t)(p + p * p) * 8))) return rc;
+    KMG_CUDA_CHECK(cudaMemcpyAsync(didx.p, idx, (size_t)nfit * 8, cudaMemcpyHostToDevice, s));
+    KMG_CUDA_CHECK(cudaMemcpyAsync(dy.p, y, (size_t)nfit * 8, cudaMemcpyHostToDevice, s));
+    for (int i = 0; i < p; ++i) {
+        if ((rc = kc[i].alloc((size_t)nfit * nfit * 8))) return rc;
+        KMG_CUDA_CHECK(cudaMemcpyAsync(full.p, Ks[i], (size_t)n * n * 8, cudaMemcpyHostToDevice, s));
+        if ((rc = kmg_ew_gather(full.as<double>(), n, didx.as<int64_t>(), nfit, sub.as<double>(), nfit, s))) return rc;   // ALIGNF.py:28
+        if ((rc = kmg_ew_center(sub.as<double>(), nfit, nfit, kc[i].as<double>(), nfit, ws.p, s))) return rc;              // ALIGNF.py:36-41
+        // a_i = sum(Kc_i * y y')  (ALIGNF.py:43-48)
+        if ((rc = kmg_ew_weighted_dot(kc[i].as<double>(), nfit, nullptr, 0, dy.as<double>(), nfit, part.as<double>(), res.as<double>() + i, s))) return rc;
+        KMG_CUDA_CHECK(cudaStreamSynchronize(s));  // `full` is reused by the next kernel's upload
+    }
+    for (int i = 0; i < p; ++i)
+        for (int j = i; j < p; ++j)  // M_ij = sum(Kc_i * Kc_j)  (ALIGNF.py:50-58)
+            if ((rc = kmg_ew_weighted_dot(kc[i].as<double>(), nfit, kc[j].as<double>(), nfit, nullptr, nfit, part.as<double>(),
+                                          res.as<double>() + p + i * p + j, s))) return rc;
+    std::vector<double> h((size_t)(p + p * p), 0.0);
+    KMG_CUDA_CHECK(cudaMemcpyAsync(h.data(), res.p, h.size() * 8, cudaMemcpyDeviceToHost, s));
+    KMG_CUDA_CHECK(cudaStreamSynchronize(s));
+    for (int i = 0; i < p; ++i) a[i] = h[i];
+    for (int i = 0; i < p; ++i)
+        for (int j = i; j < p; ++j) M[i * p + j] = M[j * p + i] = h[p + i * p + j];
+    return KMG_OK;
+}
+
+int kmg_nlck_grad_host(const double* const* Ks_fit, int p, int64_t nfit, const double* u, const double* alpha, int degree,
+                       double* grad) {
+    int rc = require_device();
+    if (rc) return rc;
+    KMG_REQUIRE(p >= 1 && p <= KMG_MAX_COMBINE && nfit >= 0 && Ks_fit && u && alpha && grad && degree >= 1, KMG_ERR_ARG, "nlck_grad: bad arguments");
+    if (nfit == 0) { for (int m = 0; m < p; ++m) grad[m] = 0.0; return KMG_OK; }
+    cudaStream_t s;
+    if ((rc = get_streams(&s, nullptr))) return rc;
+    std::vector<DevBuf> bufs(p);
+    const double* dptr[KMG_MAX_COMBINE];
+    int64_t lds[KMG_MAX_COMBINE];
+    for (int m = 0; m < p; ++m) {
+        if ((rc = bufs[m].alloc((size_t)nfit * nfit * 8))) return rc;
+        KMG_CUDA_CHECK(cudaMemcpyAsync(bufs[m].p, Ks_fit[m], (size_t)nfit * nfit * 8, cudaMemcpyHostToDevice, s));
+        dptr[m] = bufs[m].as<double>();
+        lds[m] = nfit;
+    }
+    DevBuf kt, da, part, res;
+    if ((rc = kt.alloc((size_t)nfit * nfit * 8))) return rc;
+    if ((rc = da.alloc((size_t)nfit * 8))) return rc;
+    if ((rc = part.alloc((size_t)nfit * 8))) return rc;
+    if ((rc = res.alloc((size_t)p * 8))) return rc;
+    KMG_CUDA_CHECK(cudaMemcpyAsync(da.p, alpha, (size_t)nfit * 8, cudaMemcpyHostToDevice, s));
+    // K_t = (sum_m u_m K_m) ** (degree - 1)   (NLCKernels.py:62)
+    if ((rc = kmg_ew_combine(dptr, lds, u, p, degree - 1, nfit, nfit, kt.as<double>(), nfit, s))) return rc;
+    for (int m = 0; m < p; ++m)  // alpha' (K_t * K_m) alpha  (NLCKernels.py:65)
+        if ((rc = kmg_ew_weighted_dot(kt.as<double>(), nfit, dptr[m], nfit, da.as<double>(), nfit, part.as<double>(), res.as<double>() + m, s))) return rc;
+    std::vector<double> h((size_t)p);
+    KMG_CUDA_CHECK(cudaMemcpyAsync(h.data(), res.p, (size_t)p * 8, cudaMemcpyDeviceToHost, s));
+    KMG_CUDA_CHECK(cudaStreamSynchronize(s));
+    for (int m = 0; m < p; ++m) grad[m] = -(double)degree * h[m];  // NLCKernels.py:66
+    return KMG_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// device-pointer entry points
+// ------------------------------------------------------------------------------------------
+int kmg_pack_dev(const uint8_t* d_seqs, int seq_format, int64_t n, int L, uint32_t* d_planes, int* d_err_flag, void* stream) {
+    return kmg_pack_launch(d_seqs, seq_format == KMG_SEQ_ASCII, n, L, d_planes, d_err_flag, (cudaStream_t)stream);
+}
+
+int64_t kmg_spectrum_phi_width(const int* ks, int nk) { return kmg_spectrum_padded_width(ks, nk, 0); }
+
+int kmg_spectrum_phi_dev(const uint32_t* d_planes, int64_t n, int L, const int* ks, int nk, int8_t* d_phi, int64_t ld_phi,
+                         void* stream) {
+    return kmg_spectrum_phi_launch(d_planes, n, L, ks, nk, d_phi, ld_phi, (cudaStream_t)stream);
+}
+
+int kmg_gram_i8_dev(const int8_t* d_phi_rows, const int8_t* d_phi_cols, int64_t rows, int64_t cols, int64_t width,
+                    int64_t ld_phi, int64_t row_index0, int64_t col_index0, void* d_out, int64_t ldo, int out_dtype,
+                    int symmetric, const double* d_sd_rows, const double* d_sd_cols, int m_sub, void* stream) {
+    KMG_REQUIRE(out_dtype == KMG_OUT_S32 || out_dtype == KMG_OUT_F64, KMG_ERR_ARG, "gram_i8: bad out_dtype");
+    KMG_REQUIRE(!(d_sd_rows && out_dtype != KMG_OUT_F64), KMG_ERR_ARG, "gram_i8: normalisation needs the f64 output");
+    KMG_REQUIRE((d_sd_rows == nullptr) == (d_sd_cols == nullptr), KMG_ERR_ARG, "gram_i8: sd_rows and sd_cols go together");
+    if (symmetric)
+        KMG_REQUIRE(rows == cols && row_index0 == col_index0 && d_phi_rows == d_phi_cols, KMG_ERR_ARG,
+                    "gram_i8: symmetric mode needs a square diagonal block of one Phi");
+    if (rows == 0 || cols == 0) return KMG_OK;
+    GramI8Args a;
+    memset(&a, 0, sizeof(a));
+    a.phi_rows = d_phi_rows; a.phi_cols = d_phi_cols; a.rows = rows; a.cols = cols; a.Dpad = width; a.ld_phi = ld_phi;
+    a.row_index0 = row_index0; a.col_index0 = col_index0; a.out = d_out; a.ldo = ldo; a.out_dtype = out_dtype;
+    a.symmetric = symmetric; a.out_t = d_out; a.ldo_t = ldo; a.sd_rows = d_sd_rows; a.sd_cols = d_sd_cols; a.m_sub = m_sub;
+    return kmg_gram_i8_launch(&a, (cudaStream_t)stream);
+}
+
+int kmg_gram_i8_simt_dev(const int8_t* d_phi_rows, const int8_t* d_phi_cols, int64_t rows, int64_t cols, int64_t width,
+                         int64_t ld_phi, int32_t* d_out, int64_t ldo, void* stream) {
+    return kmg_gram_i8_simt_launch(d_phi_rows, d_phi_cols, ld_phi, rows, cols, width, d_out, ldo, (cudaStream_t)stream);
+}
+
+int kmg_mismatch_phi_dev(const uint32_t* d_planes, int64_t n, int L, int k, int m, int8_t* d_phi, int64_t ld_phi, void* stream) {
+    return kmg_mismatch_phi_launch(d_planes, n, L, k, m, d_phi, ld_phi, (cudaStream_t)stream);
+}
+
+int kmg_phi_diag_sqrt_dev(const int8_t* d_phi, int64_t n, int64_t width, int64_t ld_phi, double* d_sd, void* stream) {
+    return kmg_phi_diag_sqrt_launch(d_phi, n, width, ld_phi, d_sd, (cudaStream_t)stream);
+}
+
+static PairBlock make_block(const uint32_t* pr, const uint32_t* pc, int64_t rows, int64_t cols, int64_t r0, int64_t c0, int L,
+                            void* out, int64_t ldo, int dtype, int symmetric, const double* sdr, const double* sdc) {
+    PairBlock b;
+    memset(&b, 0, sizeof(b));
+    b.planes_rows = pr; b.planes_cols = pc; b.rows = rows; b.cols = cols; b.row_index0 = r0; b.col_index0 = c0; b.L = L;
+    b.out = out; b.ldo = ldo; b.out_dtype = dtype; b.symmetric = symmetric; b.out_t = out; b.ldo_t = ldo;
+    b.sd_rows = sdr; b.sd_cols = sdc;
+    return b;
+}
+
+int kmg_mismatch_dev(const uint32_t* d_planes_rows, const uint32_t* d_planes_cols, int64_t rows, int64_t cols,
+                     int64_t row_index0, int64_t col_index0, int L, int k, int m, void* d_out, int64_t ldo, int out_dtype,
+                     int symmetric, const double* d_sd_rows, const double* d_sd_cols, void* stream) {
+    KMG_REQUIRE(out_dtype == KMG_OUT_S32 || out_dtype == KMG_OUT_F64, KMG_ERR_ARG, "mismatch: bad out_dtype");
+    KMG_REQUIRE(!(d_sd_rows && out_dtype != KMG_OUT_F64), KMG_ERR_ARG, "mismatch: normalisation needs the f64 output");
+    KMG_REQUIRE((d_sd_rows == nullptr) == (d_sd_cols == nullptr), KMG_ERR_ARG, "mismatch: sd_rows and sd_cols go together");
+    PairBlock b = make_block(d_planes_rows, d_planes_cols, rows, cols, row_index0, col_index0, L, d_out, ldo, out_dtype, symmetric,
+                             d_sd_rows, d_sd_cols);
+    return kmg_mismatch_launch(&b, k, m, (cudaStream_t)stream);
+}
+
+int kmg_mismatch_diag_dev(const uint32_t* d_planes, int64_t n, int L, int k, int m, double* d_sd, void* stream) {
+    return kmg_mismatch_diag_launch(d_planes, n, L, k, m, d_sd, (cudaStream_t)stream);
+}
+
+int kmg_wd_dev(const uint32_t* d_planes_rows, const uint32_t* d_planes_cols, int64_t rows, int64_t cols, int64_t row_index0,
+               int64_t col_index0, int L, int d, double* d_out, int64_t ldo, int symmetric, void* stream) {
+    PairBlock b = make_block(d_planes_rows, d_planes_cols, rows, cols, row_index0, col_index0, L, d_out, ldo, KMG_OUT_F64, symmetric,
+                             nullptr, nullptr);
+    return kmg_wd_launch(&b, d, (cudaStream_t)stream);
+}
+
+int kmg_la_dev(const uint32_t* d_planes_rows, const uint32_t* d_planes_cols, int64_t rows, int64_t cols, int64_t row_index0,
+               int64_t col_index0, int L, double e, double d, double beta, int smith, double* d_out, int64_t ldo,
+               int symmetric, void* stream) {
+    PairBlock b = make_block(d_planes_rows, d_planes_cols, rows, cols, row_index0, col_index0, L, d_out, ldo, KMG_OUT_F64, symmetric,
+                             nullptr, nullptr);
+    return kmg_la_launch(&b, e, d, beta, smith, (cudaStream_t)stream);
+}
+
+int kmg_normalize_dev(double* d_K, int64_t n, int64_t ld, double* d_sd_scratch, void* stream) {
+    int rc = kmg_ew_diag_sqrt(d_K, n, ld, d_sd_scratch, (cudaStream_t)stream);
+    if (rc) return rc;
+    return kmg_ew_normalize(d_K, n, ld, d_sd_scratch, (cudaStream_t)stream);
+}
+
+int64_t kmg_center_workspace_bytes(int64_t n) { return kmg_ew_center_workspace(n); }
+
+int kmg_center_dev(const double* d_K, int64_t n, int64_t ld, double* d_out, int64_t ldo, void* d_workspace, void* stream) {
+    return kmg_ew_center(d_K, n, ld, d_out, ldo, d_workspace, (cudaStream_t)stream);
+}
+
+int kmg_gather_dev(const double* d_K, int64_t ld, const int64_t* d_idx, int64_t m, double* d_out, int64_t ldo, void* stream) {
+    return kmg_ew_gather(d_K, ld, d_idx, m, d_out, ldo, (cudaStream_t)stream);
+}
+
+int kmg_combine_dev(const double* const* d_Ks, const int64_t* lds, const double* u, int p, int degree, int64_t rows, int64_t cols,
+                    double* d_out, int64_t ldo, void* stream) {
+    return kmg_ew_combine(d_Ks, lds, u, p, degree, rows, cols, d_out, ldo, (cudaStream_t)stream);
+}
+
+int kmg_weighted_dot_dev(const double* d_A, int64_t lda, const double* d_B, int64_t ldb, const double* d_w, int64_t n,
+                         double* d_partial, double* d_result, void* stream) {
+    return kmg_ew_weighted_dot(d_A, lda, d_B, ldb, d_w, n, d_partial, d_result, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,241 @@
+// elementwise.cu -- HBM-bound passes over stored fp64 Grams: cosine normalisation, centring,
+// sub-block gather, linear / polynomial kernel combination and the Frobenius / quadratic-form
+// reductions ALIGNF and NLCK need.
+//
+//   normalize_K  kernels.py:398-415      center_K   kernels.py:387-395
+//   ALIGNF       ALIGNF.py:28 (sub-block), :36-41 (centre), :43-48 (a), :50-58 (M), :91-94 (sum u_i K_i)
+//   NLCK         NLCKernels.py:43-48 (normalise), :52 and :97 ((sum u_m K_m)**degree), :61-66 (grad)
+//
+// All kernels stream the matrices once with fully coalesced 8-byte accesses; reductions are
+// deterministic two-stage trees (no atomics), so repeated runs are bit-identical.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "elementwise.h"
+#include "kmg_common.cuh"
+
+namespace {
+
+__global__ void diag_sqrt_kernel(const double* __restrict__ K, int64_t n, int64_t ld, double* __restrict__ sd) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) sd[i] = sqrt(K[i * ld + i]);  // np.sqrt(np.diag(K)), kernels.py:408
+}
+
+// In place.  Only upper-triangle 32x32 tiles run; each reads K[i,j] (i<j), writes the quotient to
+// (i,j) and -- through a shared-memory transpose -- to (j,i), exactly the mirror of kernels.py:412-413.
+__global__ void __launch_bounds__(256) normalize_kernel(double* __restrict__ K, int64_t n, int64_t ld, const double* __restrict__ sd) {
+    const int64_t bi = blockIdx.y, bj = blockIdx.x;
+    if (bj < bi) return;
+    __shared__ double tile[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+    for (int rr = ty; rr < 32; rr += 8) {
+        const int64_t i = bi * 32 + rr, j = bj * 32 + tx;
+        double v = 0.0;
+        if (i < n && j < n) {
+            if (i < j) {
+                v = __ddiv_rn(K[i * ld + j], __dmul_rn(sd[i], sd[j]));
+                K[i * ld + j] = v;
+            } else if (i == j) {
+                v = 1.0;
+                K[i * ld + j] = 1.0;  // np.fill_diagonal(K, 1), kernels.py:414
+            }
+        }
+        tile[rr][tx] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int rr = ty; rr < 32; rr += 8) {
+        // element (j', i') of the mirrored tile = tile[i'][j']
+        const int64_t jrow = bj * 32 + rr, icol = bi * 32 + tx;
+        if (jrow < n && icol < n && icol < jrow) K[jrow * ld + icol] = tile[tx][rr];
+    }
+}
+
+// row sums: one warp per row
+__global__ void __launch_bounds__(256) row_sum_kernel(const double* __restrict__ K, int64_t rows, int64_t cols, int64_t ld,
+                                                      double* __restrict__ rs) {
+    const int64_t row = blockIdx.x * 8ll + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    double acc = 0.0;
+    for (int64_t j = lane; j < cols; j += 32) acc += K[row * ld + j];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) rs[row] = acc;
+}
+
+// column sums, stage 1: thread owns a column, block owns a 256-column x CHUNK-row slab
+constexpr int CS_CHUNK = 256;
+__global__ void __launch_bounds__(256) col_sum_partial_kernel(const double* __restrict__ K, int64_t rows, int64_t cols, int64_t ld,
+                                                              double* __restrict__ part) {
+    const int64_t j = blockIdx.x * 256ll + threadIdx.x;
+    const int64_t i0 = (int64_t)blockIdx.y * CS_CHUNK;
+    if (j >= cols) return;
+    const int64_t i1 = (i0 + CS_CHUNK < rows) ? i0 + CS_CHUNK : rows;
+    double acc = 0.0;
+    for (int64_t i = i0; i < i1; ++i) acc += K[i * ld + j];
+    part[(int64_t)blockIdx.y * cols + j] = acc;
+}
+__global__ void col_sum_final_kernel(const double* __restrict__ part, int64_t nchunks, int64_t cols, double* __restrict__ cs) {
+    const int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (j >= cols) return;
+    double acc = 0.0;
+    for (int64_t c = 0; c < nchunks; ++c) acc += part[c * cols + j];
+    cs[j] = acc;
+}
+
+__device__ __forceinline__ double block_sum(double v, double* sh) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) sh[w] = v;
+    __syncthreads();
+    v = (threadIdx.x < (blockDim.x >> 5)) ? sh[threadIdx.x] : 0.0;
+    if (w == 0) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    }
+    __syncthreads();
+    return v;  // valid in thread 0
+}
+
+__global__ void __launch_bounds__(256) vec_sum_kernel(const double* __restrict__ v, int64_t n, double* __restrict__ out) {
+    __shared__ double sh[8];
+    double acc = 0.0;
+    for (int64_t i = threadIdx.x; i < n; i += 256) acc += v[i];
+    acc = block_sum(acc, sh);
+    if (threadIdx.x == 0) *out = acc;
+}
+
+// out[i,j] = K[i,j] - cs[j]/n - rs[i]/n + g/n^2   (closed form of (I-11'/n) K (I-11'/n))
+__global__ void __launch_bounds__(256) center_apply_kernel(const double* __restrict__ K, int64_t n, int64_t ld,
+                                                           const double* __restrict__ rs, const double* __restrict__ cs,
+                                                           const double* __restrict__ g, double* __restrict__ out, int64_t ldo) {
+    const int64_t j = blockIdx.x * 256ll + threadIdx.x;
+    const int64_t i = blockIdx.y;
+    if (j >= n) return;
+    const double inv = 1.0 / (double)n;
+    out[i * ldo + j] = K[i * ld + j] - cs[j] * inv - rs[i] * inv + (*g) * inv * inv;
+}
+
+__global__ void __launch_bounds__(256) gather_kernel(const double* __restrict__ K, int64_t ld, const int64_t* __restrict__ idx,
+                                                     int64_t m, double* __restrict__ out, int64_t ldo) {
+    const int64_t b = blockIdx.x * 256ll + threadIdx.x;
+    const int64_t a = blockIdx.y;
+    if (b >= m) return;
+    out[a * ldo + b] = K[idx[a] * ld + idx[b]];
+}
+
+struct CombineParams {
+    int p;
+    int degree;
+    const double* K[KMG_MAX_COMBINE];
+    int64_t ld[KMG_MAX_COMBINE];
+    double u[KMG_MAX_COMBINE];
+};
+
+// out = (sum_m u_m K_m) ** degree, products and sums rounded separately in the order numpy uses
+// (np.sum(kernels * u[:,None,None], axis=0): K_0 u_0, then + K_1 u_1, ...).
+__global__ void __launch_bounds__(256) combine_kernel(CombineParams cp, int64_t rows, int64_t cols, double* __restrict__ out, int64_t ldo) {
+    const int64_t j = blockIdx.x * 256ll + threadIdx.x;
+    const int64_t i = blockIdx.y;
+    if (j >= cols || i >= rows) return;
+    double acc = __dmul_rn(cp.K[0][i * cp.ld[0] + j], cp.u[0]);
+    for (int m = 1; m < cp.p; ++m) acc = __dadd_rn(acc, __dmul_rn(cp.K[m][i * cp.ld[m] + j], cp.u[m]));
+    double v = acc;
+    if (cp.degree == 0) v = 1.0;
+    else if (cp.degree == 2) v = __dmul_rn(acc, acc);  // numpy: x**2 -> np.square
+    else if (cp.degree != 1) v = pow(acc, (double)cp.degree);
+    out[i * ldo + j] = v;
+}
+
+// partial[b] = sum over the block's elements of A_ij * (B ? B_ij : 1) * (w ? w_i w_j : 1)
+__global__ void __launch_bounds__(256) weighted_dot_partial_kernel(const double* __restrict__ A, int64_t lda, const double* __restrict__ B,
+                                                                   int64_t ldb, const double* __restrict__ w, int64_t n,
+                                                                   double* __restrict__ partial) {
+    __shared__ double sh[8];
+    const int64_t i = blockIdx.x;
+    double acc = 0.0;
+    const double wi = w ? w[i] : 1.0;
+    for (int64_t j = threadIdx.x; j < n; j += 256) {
+        double v = A[i * lda + j];
+        if (B) v *= B[i * ldb + j];
+        if (w) v *= w[j];
+        acc += v;
+    }
+    acc = block_sum(acc, sh);
+    if (threadIdx.x == 0) partial[i] = acc * wi;
+}
+
+}  // namespace
+
+int kmg_ew_diag_sqrt(const double* K, int64_t n, int64_t ld, double* sd, cudaStream_t s) {
+    if (n <= 0) return KMG_OK;
+    diag_sqrt_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(K, n, ld, sd);
+    KMG_CUDA_CHECK(cudaGetLastError());
+    return KMG_OK;
+}
+
+int kmg_ew_normalize(double* K, int64_t n, int64_t ld, const double* sd, cudaStream_t s) {
+    if (n <= 0) return KMG_OK;
+    const unsigned t = (unsigned)((n + 31) / 32);
+    KMG_REQUIRE(t <= 65535, KMG_ERR_ARG, "normalize: n too large for one launch");
+    normalize_kernel<<<dim3(t, t), 256, 0, s>>>(K, n, ld, sd);
+    KMG_CUDA_CHECK(cudaGetLastError());
+    return KMG_OK;
+}
+
+int64_t kmg_ew_center_workspace(int64_t n) {
+    const int64_t chunks = (n + CS_CHUNK - 1) / CS_CHUNK;
+    return (chunks * n + 2 * n + 8) * (int64_t)sizeof(double);
+}
+
+int kmg_ew_center(const double* K, int64_t n, int64_t ld, double* out, int64_t ldo, void* workspace, cudaStream_t s) {
+    if (n <= 0) return KMG_OK;
+    KMG_REQUIRE(n <= 65535ll * 8, KMG_ERR_ARG, "center: n too large for one launch");
+    const int64_t chunks = (n + CS_CHUNK - 1) / CS_CHUNK;
+    double* part = reinterpret_cast<double*>(workspace);
+    double* rs = part + chunks * n;
+    double* cs = rs + n;
+    double* g = cs + n;
+    row_sum_kernel<<<(unsigned)((n + 7) / 8), 256, 0, s>>>(K, n, n, ld, rs);
+    col_sum_partial_kernel<<<dim3((unsigned)((n + 255) / 256), (unsigned)chunks), 256, 0, s>>>(K, n, n, ld, part);
+    col_sum_final_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(part, chunks, n, cs);
+    vec_sum_kernel<<<1, 256, 0, s>>>(rs, n, g);
+    center_apply_kernel<<<dim3((unsigned)((n + 255) / 256), (unsigned)n), 256, 0, s>>>(K, n, ld, rs, cs, g, out, ldo);
+    KMG_CUDA_CHECK(cudaGetLastError());
+    return KMG_OK;
+}
+
+int kmg_ew_gather(const double* K, int64_t ld, const int64_t* idx, int64_t m, double* out, int64_t ldo, cudaStream_t s) {
+    if (m <= 0) return KMG_OK;
+    KMG_REQUIRE(m <= 65535, KMG_ERR_ARG, "gather: sub-block too large for one launch");
+    gather_kernel<<<dim3((unsigned)((m + 255) / 256), (unsigned)m), 256, 0, s>>>(K, ld, idx, m, out, ldo);
+    KMG_CUDA_CHECK(cudaGetLastError());
+    return KMG_OK;
+}
+
+int kmg_ew_combine(const double* const* Ks, const int64_t* lds, const double* u, int p, int degree, int64_t rows, int64_t cols,
+                   double* out, int64_t ldo, cudaStream_t s) {
+    KMG_REQUIRE(p >= 1 && p <= KMG_MAX_COMBINE, KMG_ERR_ARG, "combine: between 1 and %d kernels", KMG_MAX_COMBINE);
+    KMG_REQUIRE(degree >= 0 && degree <= 64, KMG_ERR_ARG, "combine: degree out of range");
+    if (rows <= 0 || cols <= 0) return KMG_OK;
+    KMG_REQUIRE(rows <= 65535, KMG_ERR_ARG, "combine: too many rows for one launch");
+    CombineParams cp;
+    cp.p = p; cp.degree = degree;
+    for (int m = 0; m < p; ++m) { cp.K[m] = Ks[m]; cp.ld[m] = lds[m]; cp.u[m] = u[m]; }
+    combine_kernel<<<dim3((unsigned)((cols + 255) / 256), (unsigned)rows), 256, 0, s>>>(cp, rows, cols, out, ldo);
+    KMG_CUDA_CHECK(cudaGetLastError());
+    return KMG_OK;
+}
+
+int kmg_ew_weighted_dot(const double* A, int64_t lda, const double* B, int64_t ldb, const double* w, int64_t n, double* partial,
+                        double* result, cudaStream_t s) {
+    if (n <= 0) return KMG_OK;
+    weighted_dot_partial_kernel<<<(unsigned)n, 256, 0, s>>>(A, lda, B, ldb, w, n, partial);
+    vec_sum_kernel<<<1, 256, 0, s>>>(partial, n, result);
+    KMG_CUDA_CHECK(cudaGetLastError());
+    return KMG_OK;
+}

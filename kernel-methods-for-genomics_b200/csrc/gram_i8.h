@@ -1,0 +1,31 @@
+// gram_i8.h -- internal launch interface of the tcgen05 int8 Gram GEMM (gram_i8_tcgen05.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define KMG_OUT_S32 0
+#define KMG_OUT_F64 1
+
+struct GramI8Args {
+    const int8_t* phi_rows;  // first row of the row block of Phi (device)
+    const int8_t* phi_cols;  // first row of the column block of Phi (device)
+    int64_t rows, cols;      // block shape
+    int64_t Dpad;            // feature width, multiple of 128 (zero padded)
+    int64_t ld_phi;          // bytes between rows of Phi
+    int64_t row_index0, col_index0;  // global indices of the block origin (diagonal detection)
+    void* out;               // rows x cols, element stride ldo
+    int64_t ldo;
+    int out_dtype;           // KMG_OUT_S32 / KMG_OUT_F64
+    int symmetric;           // 1: square diagonal block, compute tiles touching col >= row and mirror-store the rest
+    void* out_t;             // mirror destination: element (r,c) -> out_t[c*ldo_t + r] (== out for an in-place full Gram)
+    int64_t ldo_t;
+    const double* sd_rows;   // optional cosine normalisation: sqrt(diag) for the block's rows / cols
+    const double* sd_cols;
+    int m_sub;               // 0 = auto, 1 = 128x256 tiles, 2 = 256x256 tiles
+    int max_ctas;            // 0 = all SMs
+    int64_t* computed_entries;  // optional out: entries actually issued to the tensor cores
+};
+
+int kmg_gram_i8_launch(const GramI8Args* a, cudaStream_t stream);
+int kmg_gram_i8_simt_launch(const int8_t* A, const int8_t* B, int64_t ld, int64_t rows, int64_t cols, int64_t Dpad,
+                            int32_t* out, int64_t ldo, cudaStream_t stream);

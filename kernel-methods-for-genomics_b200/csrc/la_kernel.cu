@@ -1,0 +1,243 @@
+// la_kernel.cu -- Vert-Saigo local-alignment kernel, anti-diagonal wavefront DP, one warp per pair.
+//
+// Reference: affine_align / Smith_Waterman / get_LA_K (kernels.py:226-302).  AS WRITTEN the
+// reference returns exactly 0.0 for every pair (its five DP matrices are one aliased array,
+// kernels.py:238, and the loops never reach the cell that is read); that behaviour
+// is reproduced on the host side (kernels.LA_REFERENCE_COMPAT) without a kernel.  This file
+// implements the INTENDED recursion, which is the measurable work:
+//
+//   M [i,j] = e^{b s(x_i,y_j)} (1 + X[i-1,j-1] + Y[i-1,j-1] + M[i-1,j-1])
+//   X [i,j] = e^{b d} M[i-1,j] + e^{b e} X[i-1,j]
+//   Y [i,j] = e^{b d} (M[i,j-1] + X[i,j-1]) + e^{b e} Y[i,j-1]
+//   X2[i,j] = M[i-1,j] + X2[i-1,j]
+//   Y2[i,j] = M[i,j-1] + X2[i,j-1] + Y2[i,j-1]
+//   K(x,y)  = (1/b) ln(1 + X2 + Y2 + M)[n_x, n_y]
+//
+// Lane l owns rows 4l+1..4l+4 and walks the columns skewed by one step per lane (lane l is on
+// column t-l+1 at step t), so the warp sweeps anti-diagonal bands; the row above a lane's strip
+// arrives by __shfl_up from the lane that computed it one step earlier.
+//
+// Numerics: with the reference's default parameters (e=11, d=1, beta=0.5, taken literally as
+// e^{+b e}) the linear-space values overflow fp64 within ~90 cells, so the state is kept in fp64
+// scaled by a warp-wide power of two 2^-E: whenever the largest live value exceeds 2^64 every live
+// value is multiplied by an exact power of two and E is bumped (error-free).  The result is
+// (ln(sum_scaled) + E ln 2)/b.  This is mathematically the log-space evaluation the north star
+// asks for at ~1/50th of the flops of a literal log-sum-exp per cell.  Smith-Waterman (max-plus)
+// runs directly in log space (adds and maxes only).
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "gram_i8.h"
+#include "kmg_common.cuh"
+#include "pair_kernels.h"
+
+namespace {
+
+constexpr int LA_WARPS = 8;
+constexpr int ROWS_PER_LANE = 4;
+
+struct LaParams {
+    int L;
+    int smith;
+    double inv_beta;
+    double ed, ee;      // e^{beta d}, e^{beta e}    (affine)
+    double bd, be;      // beta d, beta e            (smith)
+    double sub[16];     // affine: e^{beta S[a][b]};  smith: beta S[a][b]   (S = kernels.py:223, index [x][y])
+    int64_t rows, cols, row_index0, col_index0;
+    int symmetric;
+    double* out;
+    int64_t ldo;
+    double* out_t;
+    int64_t ldo_t;
+};
+
+__device__ __forceinline__ int code_at(const SeqPlanes& s, int pos) {
+    // pos is lane-dependent: select the word without dynamic register indexing
+    const int w = pos >> 5, b = pos & 31;
+    const uint32_t lo = w == 0 ? s.lo[0] : (w == 1 ? s.lo[1] : (w == 2 ? s.lo[2] : s.lo[3]));
+    const uint32_t hi = w == 0 ? s.hi[0] : (w == 1 ? s.hi[1] : (w == 2 ? s.hi[2] : s.hi[3]));
+    return (int)(((lo >> b) & 1u) | (((hi >> b) & 1u) << 1));
+}
+
+__device__ __forceinline__ double shfl_up_d(double v) { return __shfl_up_sync(0xffffffffu, v, 1); }
+
+__global__ void __launch_bounds__(LA_WARPS * 32)
+la_kernel(const uint32_t* __restrict__ prow, const uint32_t* __restrict__ pcol, const LaParams p) {
+    __shared__ uint8_t ycode_s[LA_WARPS][KMG_MAX_L];
+    __shared__ double sub_s[16];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x < 16) sub_s[threadIdx.x] = p.sub[threadIdx.x];
+    __syncthreads();
+    const int64_t pair = (int64_t)blockIdx.x * LA_WARPS + warp;
+    if (pair >= p.rows * p.cols) return;
+    const int64_t r = pair / p.cols, c = pair % p.cols;
+    const int64_t gr = p.row_index0 + r, gc = p.col_index0 + c;
+    if (p.symmetric && gc < gr) return;  // produced by the mirror store of (c, r)
+    // kernels.py:289-291: K[i,j] is evaluated with x = row i, y = row j for j >= i, then mirrored
+    const bool swap = gc < gr;
+    const SeqPlanes xs = swap ? kmg_load_planes(pcol, c) : kmg_load_planes(prow, r);
+    const SeqPlanes ys = swap ? kmg_load_planes(prow, r) : kmg_load_planes(pcol, c);
+    const int L = p.L;
+    for (int j = lane; j < KMG_MAX_L; j += 32) ycode_s[warp][j] = (uint8_t)code_at(ys, j);
+    __syncwarp();
+    int xc[ROWS_PER_LANE];
+#pragma unroll
+    for (int q = 0; q < ROWS_PER_LANE; ++q) xc[q] = code_at(xs, (lane * ROWS_PER_LANE + q) & 127) << 2;
+
+    const int last_lane = (L - 1) / ROWS_PER_LANE, last_q = (L - 1) % ROWS_PER_LANE;
+    const int steps = L + 31;
+    double result = 0.0;
+
+    if (!p.smith) {
+        // ---------------- affine_align, scaled linear space
+        double M[ROWS_PER_LANE], X[ROWS_PER_LANE], Y[ROWS_PER_LANE], X2[ROWS_PER_LANE], Y2[ROWS_PER_LANE];
+#pragma unroll
+        for (int q = 0; q < ROWS_PER_LANE; ++q) M[q] = X[q] = Y[q] = X2[q] = Y2[q] = 0.0;
+        double dM = 0.0, dX = 0.0, dY = 0.0;  // row above the strip, previous column
+        int E = 0;                            // stored = true * 2^-E
+        double one_s = 1.0;
+        const double ed = p.ed, ee = p.ee;
+#pragma unroll 1
+        for (int t = 0; t < steps; ++t) {
+            // bottom row of the lane above, as computed in the previous step (= this lane's column j)
+            double uM = shfl_up_d(M[ROWS_PER_LANE - 1]);
+            double uX = shfl_up_d(X[ROWS_PER_LANE - 1]);
+            double uY = shfl_up_d(Y[ROWS_PER_LANE - 1]);
+            double uX2 = shfl_up_d(X2[ROWS_PER_LANE - 1]);
+            if (lane == 0) uM = uX = uY = uX2 = 0.0;
+            const int j = t - lane;  // 0-based column
+            const bool active = j >= 0 && j < L;
+            if (active) {
+                const int yc = ycode_s[warp][j];
+                double aM = uM, aX = uX, aY = uY, aX2 = uX2;  // "up"   : (i-1, j)
+                double gM = dM, gX = dX, gY = dY;             // "diag" : (i-1, j-1)
+#pragma unroll
+                for (int q = 0; q < ROWS_PER_LANE; ++q) {
+                    const double a = sub_s[xc[q] | yc];
+                    const double lM = M[q], lX = X[q], lY = Y[q], lX2 = X2[q], lY2 = Y2[q];  // "left": (i, j-1)
+                    const double nM = a * (((one_s + gX) + gY) + gM);
+                    const double nX = ed * aM + ee * aX;
+                    const double nY = ed * (lM + lX) + ee * lY;
+                    const double nX2 = aM + aX2;
+                    const double nY2 = (lM + lX2) + lY2;
+                    gM = lM; gX = lX; gY = lY;
+                    aM = nM; aX = nX; aY = nY; aX2 = nX2;
+                    M[q] = nM; X[q] = nX; Y[q] = nY; X2[q] = nX2; Y2[q] = nY2;
+                }
+                (void)aY;
+                dM = uM; dX = uX; dY = uY;
+            }
+            if (t == L - 1 + last_lane && lane == last_lane) {
+                // cell (n_x, n_y): this lane's row last_q at column L-1
+                double m = M[0], x2 = X2[0], y2 = Y2[0];
+#pragma unroll
+                for (int q = 1; q < ROWS_PER_LANE; ++q)
+                    if (q == last_q) { m = M[q]; x2 = X2[q]; y2 = Y2[q]; }
+                const double tot = ((one_s + x2) + y2) + m;
+                result = p.inv_beta * (log(tot) + (double)E * 0.6931471805599453094);
+            }
+            // ---- warp-wide power-of-two rescale (exact)
+            int hi = 0;
+#pragma unroll
+            for (int q = 0; q < ROWS_PER_LANE; ++q) {
+                hi = max(hi, __double2hiint(M[q]));
+                hi = max(hi, __double2hiint(X[q]));
+                hi = max(hi, __double2hiint(Y[q]));
+                hi = max(hi, __double2hiint(X2[q]));
+                hi = max(hi, __double2hiint(Y2[q]));
+            }
+            hi = __reduce_max_sync(0xffffffffu, hi);
+            const int ex = (hi >> 20) - 1023;  // exponent of the largest live value (all values >= 0)
+            if (ex > 64) {                     // warp-uniform
+                const double sc = __hiloint2double((1023 - ex) << 20, 0);  // 2^-ex
+#pragma unroll
+                for (int q = 0; q < ROWS_PER_LANE; ++q) {
+                    M[q] *= sc; X[q] *= sc; Y[q] *= sc; X2[q] *= sc; Y2[q] *= sc;
+                }
+                dM *= sc; dX *= sc; dY *= sc;
+                E += ex;
+                one_s = (E < 1000) ? __hiloint2double((1023 - E) << 20, 0) : 0.0;  // 2^-E (negligible beyond)
+            }
+        }
+    } else {
+        // ---------------- Smith_Waterman (max-plus), log space
+        const double NI = -INFINITY;
+        double M[ROWS_PER_LANE], X[ROWS_PER_LANE], Y[ROWS_PER_LANE], X2[ROWS_PER_LANE], Y2[ROWS_PER_LANE];
+#pragma unroll
+        for (int q = 0; q < ROWS_PER_LANE; ++q) M[q] = X[q] = Y[q] = X2[q] = Y2[q] = NI;
+        double dM = NI, dX = NI, dY = NI;
+        const double bd = p.bd, be = p.be;
+#pragma unroll 1
+        for (int t = 0; t < steps; ++t) {
+            double uM = shfl_up_d(M[ROWS_PER_LANE - 1]);
+            double uX = shfl_up_d(X[ROWS_PER_LANE - 1]);
+            double uY = shfl_up_d(Y[ROWS_PER_LANE - 1]);
+            double uX2 = shfl_up_d(X2[ROWS_PER_LANE - 1]);
+            if (lane == 0) uM = uX = uY = uX2 = NI;
+            const int j = t - lane;
+            const bool active = j >= 0 && j < L;
+            if (active) {
+                const int yc = ycode_s[warp][j];
+                double aM = uM, aX = uX, aX2 = uX2;
+                double gM = dM, gX = dX, gY = dY;
+#pragma unroll
+                for (int q = 0; q < ROWS_PER_LANE; ++q) {
+                    const double s = sub_s[xc[q] | yc];
+                    const double lM = M[q], lX = X[q], lY = Y[q], lX2 = X2[q], lY2 = Y2[q];
+                    const double nM = s + fmax(fmax(0.0, gX), fmax(gY, gM));
+                    const double nX = fmax(bd + aM, be + aX);
+                    const double nY = fmax(fmax(bd + lM, bd + lX), be + lY);
+                    const double nX2 = fmax(aM, aX2);
+                    const double nY2 = fmax(fmax(lM, lX2), lY2);
+                    gM = lM; gX = lX; gY = lY;
+                    aM = nM; aX = nX; aX2 = nX2;
+                    M[q] = nM; X[q] = nX; Y[q] = nY; X2[q] = nX2; Y2[q] = nY2;
+                }
+                dM = uM; dX = uX; dY = uY;
+            }
+            if (t == L - 1 + last_lane && lane == last_lane) {
+                double m = M[0], x2 = X2[0], y2 = Y2[0];
+#pragma unroll
+                for (int q = 1; q < ROWS_PER_LANE; ++q)
+                    if (q == last_q) { m = M[q]; x2 = X2[q]; y2 = Y2[q]; }
+                result = p.inv_beta * fmax(fmax(0.0, x2), fmax(y2, m));
+            }
+        }
+    }
+    if (lane == last_lane) {
+        p.out[r * p.ldo + c] = result;
+        if (p.symmetric && gc != gr) p.out_t[c * p.ldo_t + r] = result;
+    }
+}
+
+}  // namespace
+
+int kmg_la_launch(const PairBlock* b, double e, double d, double beta, int smith, cudaStream_t stream) {
+    KMG_REQUIRE(b->L >= 1 && b->L <= KMG_MAX_L, KMG_ERR_UNSUPPORTED, "sequence length %d not supported (1..%d)", b->L, KMG_MAX_L);
+    KMG_REQUIRE(b->out_dtype == KMG_OUT_F64 && b->sd_rows == nullptr, KMG_ERR_ARG, "local alignment Gram is raw fp64");
+    KMG_REQUIRE(beta > 0.0 && isfinite(beta) && isfinite(e) && isfinite(d), KMG_ERR_ARG, "local alignment: need finite e, d and beta > 0");
+    if (b->symmetric)
+        KMG_REQUIRE(b->rows == b->cols && b->row_index0 == b->col_index0 && b->out_t != nullptr, KMG_ERR_ARG,
+                    "symmetric mode needs a square diagonal block and a mirror destination");
+    // growth per wavefront step is at most (4 rows) * max exponent; keep it far inside the fp64 range
+    const double worst = 4.0 * beta * fmax(fmax(fabs(e), fabs(d)), 9.0) * 1.4427;
+    KMG_REQUIRE(smith || worst < 600.0, KMG_ERR_UNSUPPORTED, "local alignment: beta*max(|e|,|d|,9) too large for the scaled fp64 recursion");
+    if (b->rows == 0 || b->cols == 0) return KMG_OK;
+    static const int S[4][4] = {{4, 0, 0, 0}, {0, 9, -3, -1}, {0, -3, 6, 2}, {0, -1, -2, 5}};  // kernels.py:223
+    LaParams p;
+    p.L = b->L; p.smith = smith; p.inv_beta = 1.0 / beta;
+    p.ed = exp(beta * d); p.ee = exp(beta * e); p.bd = beta * d; p.be = beta * e;
+    for (int a = 0; a < 4; ++a)
+        for (int c = 0; c < 4; ++c) p.sub[a * 4 + c] = smith ? beta * (double)S[a][c] : exp(beta * (double)S[a][c]);
+    p.rows = b->rows; p.cols = b->cols; p.row_index0 = b->row_index0; p.col_index0 = b->col_index0;
+    p.symmetric = b->symmetric;
+    p.out = reinterpret_cast<double*>(b->out); p.ldo = b->ldo;
+    p.out_t = reinterpret_cast<double*>(b->out_t); p.ldo_t = b->ldo_t;
+    const int64_t pairs = b->rows * b->cols;
+    const int64_t blocks = (pairs + LA_WARPS - 1) / LA_WARPS;
+    KMG_REQUIRE(blocks < (1ll << 31), KMG_ERR_ARG, "local alignment: block too large for one launch");
+    la_kernel<<<(unsigned)blocks, LA_WARPS * 32, 0, stream>>>(b->planes_rows, b->planes_cols, p);
+    KMG_CUDA_CHECK(cudaGetLastError());
+    return KMG_OK;
+}

@@ -1,0 +1,168 @@
+"""
+device.py -- device-resident layer over the `*_dev` entry points of libkmg.so.
+
+PyTorch is used for plumbing only (device memory, streams, torch.distributed in dist.py): tensors
+are allocated with torch, their raw device pointers and the current CUDA stream are handed to the
+C-ABI, and all arithmetic happens in the hand-written sm_100a kernels.  Nothing here falls back to
+torch ops for the Gram entries.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _cabi
+from ._cabi import KMG_OUT_F64, KMG_OUT_S32, KMG_SEQ_ASCII, KMG_SEQ_CODES, check
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _dev():
+    if not torch.cuda.is_available():
+        raise _cabi.KmgError(_cabi.KMG_ERR_CUDA, "no CUDA device available: libkmg has no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def pack(seq_bytes, seq_format=KMG_SEQ_CODES):
+    """(n, L) uint8 host array or device tensor -> (n, 8) int32 device tensor of bit-planes."""
+    dev = _dev()
+    if isinstance(seq_bytes, np.ndarray):
+        seq_bytes = torch.from_numpy(np.ascontiguousarray(seq_bytes)).to(dev, non_blocking=True)
+    seq_bytes = seq_bytes.contiguous()
+    n, L = seq_bytes.shape
+    planes = torch.empty((n, 8), dtype=torch.int32, device=dev)
+    err = torch.zeros(1, dtype=torch.int32, device=dev)
+    check(_cabi.lib().kmg_pack_dev(_p(seq_bytes), seq_format, n, L, _p(planes), _p(err), _stream()))
+    if int(err.item()) != 0:
+        raise ValueError("libkmg: sequence contains a character outside {A,C,G,T}")
+    return planes
+
+
+def phi_width(ks):
+    ks = np.ascontiguousarray(np.atleast_1d(ks), np.int32)
+    return int(_cabi.lib().kmg_spectrum_phi_width(ks.ctypes.data_as(C.c_void_p), ks.size))
+
+
+def spectrum_phi(planes, L, ks, out=None):
+    """planes -> int8 Phi (n, W) with W = pad128(sum_k 4^k)."""
+    ks = np.ascontiguousarray(np.atleast_1d(ks), np.int32)
+    n = planes.shape[0]
+    W = phi_width(ks)
+    if out is None:
+        out = torch.empty((n, W), dtype=torch.int8, device=planes.device)
+    check(_cabi.lib().kmg_spectrum_phi_dev(_p(planes), n, L, ks.ctypes.data_as(C.c_void_p), ks.size, _p(out), W, _stream()))
+    return out
+
+
+def mismatch_phi(planes, L, k, m):
+    n = planes.shape[0]
+    W = (4 ** k + 127) // 128 * 128
+    out = torch.empty((n, W), dtype=torch.int8, device=planes.device)
+    check(_cabi.lib().kmg_mismatch_phi_dev(_p(planes), n, L, k, m, _p(out), W, _stream()))
+    return out
+
+
+def phi_diag_sqrt(phi):
+    n, W = phi.shape
+    sd = torch.empty(n, dtype=torch.float64, device=phi.device)
+    check(_cabi.lib().kmg_phi_diag_sqrt_dev(_p(phi), n, W, phi.stride(0), _p(sd), _stream()))
+    return sd
+
+
+def _out(rows, cols, dtype, device, out):
+    if out is not None:
+        return out
+    return torch.empty((rows, cols), dtype=torch.float64 if dtype == KMG_OUT_F64 else torch.int32, device=device)
+
+
+def gram_i8(phi_rows, phi_cols, row_index0=0, col_index0=0, out_dtype=KMG_OUT_F64, symmetric=False,
+            sd_rows=None, sd_cols=None, m_sub=0, out=None):
+    """Block of K = Phi_rows Phi_cols^T on the tensor cores."""
+    rows, W = phi_rows.shape
+    cols = phi_cols.shape[0]
+    out = _out(rows, cols, out_dtype, phi_rows.device, out)
+    check(_cabi.lib().kmg_gram_i8_dev(_p(phi_rows), _p(phi_cols), rows, cols, W, phi_rows.stride(0), row_index0, col_index0,
+                                      _p(out), out.stride(0), out_dtype, 1 if symmetric else 0, _p(sd_rows), _p(sd_cols),
+                                      m_sub, _stream()))
+    return out
+
+
+def gram_i8_simt(phi_rows, phi_cols):
+    rows, W = phi_rows.shape
+    cols = phi_cols.shape[0]
+    out = torch.empty((rows, cols), dtype=torch.int32, device=phi_rows.device)
+    check(_cabi.lib().kmg_gram_i8_simt_dev(_p(phi_rows), _p(phi_cols), rows, cols, W, phi_rows.stride(0), _p(out), out.stride(0), _stream()))
+    return out
+
+
+def mismatch_block(planes_rows, planes_cols, L, k, m, row_index0=0, col_index0=0, out_dtype=KMG_OUT_F64, symmetric=False,
+                   sd_rows=None, sd_cols=None, out=None):
+    rows, cols = planes_rows.shape[0], planes_cols.shape[0]
+    out = _out(rows, cols, out_dtype, planes_rows.device, out)
+    check(_cabi.lib().kmg_mismatch_dev(_p(planes_rows), _p(planes_cols), rows, cols, row_index0, col_index0, L, k, m,
+                                       _p(out), out.stride(0), out_dtype, 1 if symmetric else 0, _p(sd_rows), _p(sd_cols), _stream()))
+    return out
+
+
+def mismatch_diag_sqrt(planes, L, k, m):
+    n = planes.shape[0]
+    sd = torch.empty(n, dtype=torch.float64, device=planes.device)
+    check(_cabi.lib().kmg_mismatch_diag_dev(_p(planes), n, L, k, m, _p(sd), _stream()))
+    return sd
+
+
+def wd_block(planes_rows, planes_cols, L, d, row_index0=0, col_index0=0, symmetric=False, out=None):
+    rows, cols = planes_rows.shape[0], planes_cols.shape[0]
+    out = _out(rows, cols, KMG_OUT_F64, planes_rows.device, out)
+    check(_cabi.lib().kmg_wd_dev(_p(planes_rows), _p(planes_cols), rows, cols, row_index0, col_index0, L, d,
+                                 _p(out), out.stride(0), 1 if symmetric else 0, _stream()))
+    return out
+
+
+def la_block(planes_rows, planes_cols, L, e, d, beta, smith=0, row_index0=0, col_index0=0, symmetric=False, out=None):
+    rows, cols = planes_rows.shape[0], planes_cols.shape[0]
+    out = _out(rows, cols, KMG_OUT_F64, planes_rows.device, out)
+    check(_cabi.lib().kmg_la_dev(_p(planes_rows), _p(planes_cols), rows, cols, row_index0, col_index0, L,
+                                 float(e), float(d), float(beta), int(smith), _p(out), out.stride(0), 1 if symmetric else 0, _stream()))
+    return out
+
+
+def normalize_(K):
+    n = K.shape[0]
+    sd = torch.empty(n, dtype=torch.float64, device=K.device)
+    check(_cabi.lib().kmg_normalize_dev(_p(K), n, K.stride(0), _p(sd), _stream()))
+    return K
+
+
+def center(K):
+    n = K.shape[0]
+    ws = torch.empty(int(_cabi.lib().kmg_center_workspace_bytes(n)), dtype=torch.uint8, device=K.device)
+    out = torch.empty_like(K)
+    check(_cabi.lib().kmg_center_dev(_p(K), n, K.stride(0), _p(out), out.stride(0), _p(ws), _stream()))
+    return out
+
+
+def combine(Ks, u, degree=1):
+    p = len(Ks)
+    rows, cols = Ks[0].shape
+    ptrs = (C.c_void_p * p)(*[k.data_ptr() for k in Ks])
+    lds = np.array([k.stride(0) for k in Ks], np.int64)
+    u = np.ascontiguousarray(u, np.float64)
+    out = torch.empty((rows, cols), dtype=torch.float64, device=Ks[0].device)
+    check(_cabi.lib().kmg_combine_dev(ptrs, lds.ctypes.data_as(C.c_void_p), u.ctypes.data_as(C.c_void_p), p, int(degree),
+                                      rows, cols, _p(out), out.stride(0), _stream()))
+    return out
+
+
+def weighted_dot(A, B=None, w=None):
+    n = A.shape[0]
+    part = torch.empty(n, dtype=torch.float64, device=A.device)
+    res = torch.empty(1, dtype=torch.float64, device=A.device)
+    check(_cabi.lib().kmg_weighted_dot_dev(_p(A), A.stride(0), _p(B), 0 if B is None else B.stride(0), _p(w), n, _p(part), _p(res), _stream()))
+    return res

@@ -1,0 +1,197 @@
+"""
+host.py -- numpy-level wrappers over the `*_host` entry points of libkmg.so.
+
+Everything here is marshalling: sequences become one contiguous (n, L) byte buffer, Gram matrices
+are caller-owned C-contiguous float64 arrays, and every call ends in the C-ABI (include/kmg.h).
+No arithmetic on Gram entries happens in Python.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _cabi
+from ._cabi import KMG_SEQ_ASCII, KMG_SEQ_CODES, check
+
+
+def as_seq_buffer(seqs):
+    """-> (uint8 array (n, L), seq_format).  Accepts a pandas Series / list / array of equal-length
+    strings (ASCII path) or a 2-D uint8 array of codes 0..3."""
+    if isinstance(seqs, np.ndarray) and seqs.dtype == np.uint8 and seqs.ndim == 2:
+        return np.ascontiguousarray(seqs), KMG_SEQ_CODES
+    if hasattr(seqs, "to_numpy"):
+        seqs = seqs.to_numpy()
+    seqs = list(seqs)
+    n = len(seqs)
+    if n == 0:
+        return np.zeros((0, 1), np.uint8), KMG_SEQ_ASCII
+    L = len(seqs[0])
+    joined = "".join(seqs)
+    if len(joined) != n * L or any(len(s) != L for s in seqs):
+        raise ValueError("all sequences must have the same length")
+    try:
+        raw = joined.encode("ascii")
+    except UnicodeEncodeError as exc:
+        raise ValueError("sequence contains a character outside {A,C,G,T}") from exc
+    return np.frombuffer(raw, dtype=np.uint8).reshape(n, L), KMG_SEQ_ASCII
+
+
+def _pair(rows, cols):
+    rbuf, rfmt = as_seq_buffer(rows)
+    if cols is None:
+        return rbuf, None, rfmt, rbuf.shape[0], rbuf.shape[0]
+    cbuf, cfmt = as_seq_buffer(cols)
+    if cfmt != rfmt:
+        raise ValueError("rows and cols must use the same sequence format")
+    if rbuf.shape[0] and cbuf.shape[0] and rbuf.shape[1] != cbuf.shape[1]:
+        raise ValueError("rows and cols must have the same sequence length")
+    return rbuf, cbuf, rfmt, rbuf.shape[0], cbuf.shape[0]
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def spectrum_gram(rows, ks, cols=None):
+    """Sum over `ks` of the k-spectrum Grams (one k: get_spectrum_K, kernels.py:28-47). Unnormalised."""
+    ks = np.ascontiguousarray(np.atleast_1d(ks), np.int32)
+    rbuf, cbuf, fmt, nr, nc = _pair(rows, cols)
+    K = np.zeros((nr, nc), np.float64)
+    L = rbuf.shape[1] if nr else 1
+    check(_cabi.lib().kmg_spectrum_host(_ptr(rbuf), nr, _ptr(cbuf), 0 if cbuf is None else nc, L, fmt,
+                                        _ptr(ks), ks.size, _ptr(K), max(nc, 1)))
+    return K
+
+
+def mismatch_gram(rows, k, m, cols=None, normalize=True, algo=0):
+    """(k,m)-mismatch Gram (get_mismatch_K, kernels.py:196-217); normalize=True is the reference.
+    algo: 0 auto (dense feature map + tensor-core GEMM for k <= 8, pairwise bit-vector kernel above),
+    1 pairwise, 2 dense."""
+    rbuf, cbuf, fmt, nr, nc = _pair(rows, cols)
+    K = np.zeros((nr, nc), np.float64)
+    L = rbuf.shape[1] if nr else 1
+    check(_cabi.lib().kmg_mismatch_host(_ptr(rbuf), nr, _ptr(cbuf), 0 if cbuf is None else nc, L, fmt,
+                                        int(k), int(m), 1 if normalize else 0, int(algo), _ptr(K), max(nc, 1)))
+    return K
+
+
+def spectrum_phi(seqs, ks):
+    """get_phi_u (kernels.py:12-25) for every sequence: int8 (n, sum_k 4^k), product('ACGT') column order."""
+    ks = np.ascontiguousarray(np.atleast_1d(ks), np.int32)
+    buf, fmt = as_seq_buffer(seqs)
+    n = buf.shape[0]
+    D = int(sum(4 ** int(k) for k in ks))
+    W = (D + 127) // 128 * 128
+    phi = np.zeros((n, W), np.int8)
+    check(_cabi.lib().kmg_spectrum_phi_host(_ptr(buf), n, buf.shape[1], fmt, _ptr(ks), ks.size, _ptr(phi), W))
+    return phi[:, :D]
+
+
+def mismatch_phi(seqs, k, m):
+    """get_phi_km (kernels.py:161-175) for every sequence: int8 (n, 4^k)."""
+    buf, fmt = as_seq_buffer(seqs)
+    n = buf.shape[0]
+    D = 4 ** int(k)
+    W = (D + 127) // 128 * 128
+    phi = np.zeros((n, W), np.int8)
+    check(_cabi.lib().kmg_mismatch_phi_host(_ptr(buf), n, buf.shape[1], fmt, int(k), int(m), _ptr(phi), W))
+    return phi[:, :D]
+
+
+def wd_gram(rows, d, cols=None):
+    """Weighted-degree Gram (get_WD_K, kernels.py:84-101)."""
+    rbuf, cbuf, fmt, nr, nc = _pair(rows, cols)
+    K = np.zeros((nr, nc), np.float64)
+    L = rbuf.shape[1] if nr else 1
+    check(_cabi.lib().kmg_wd_host(_ptr(rbuf), nr, _ptr(cbuf), 0 if cbuf is None else nc, L, fmt, int(d), _ptr(K), max(nc, 1)))
+    return K
+
+
+def la_gram(rows, e, d, beta, smith=0, cols=None):
+    """Local-alignment Gram with the INTENDED recursion (kernels.py:226-291 as meant)."""
+    rbuf, cbuf, fmt, nr, nc = _pair(rows, cols)
+    K = np.zeros((nr, nc), np.float64)
+    L = rbuf.shape[1] if nr else 1
+    check(_cabi.lib().kmg_la_host(_ptr(rbuf), nr, _ptr(cbuf), 0 if cbuf is None else nc, L, fmt,
+                                  float(e), float(d), float(beta), int(smith), _ptr(K), max(nc, 1)))
+    return K
+
+
+def _square_f64(K, name):
+    if not (isinstance(K, np.ndarray) and K.dtype == np.float64 and K.ndim == 2 and K.shape[0] == K.shape[1]):
+        raise ValueError(f"{name}: expected a square float64 numpy array")
+    return K
+
+
+def normalize_inplace(K):
+    """normalize_K (kernels.py:398-415) in place on the caller's array.  Returns True on the
+    reference's early-out (K[0,0]==1, matrix untouched)."""
+    _square_f64(K, "normalize_K")
+    n = K.shape[0]
+    if K.flags.c_contiguous:
+        return check(_cabi.lib().kmg_normalize_host(_ptr(K), n, max(n, 1))) == 1
+    if K.strides[1] == 8 and K.strides[0] % 8 == 0 and K.strides[0] >= 8 * n:  # row-strided view
+        return check(_cabi.lib().kmg_normalize_host(_ptr(K), n, K.strides[0] // 8)) == 1
+    tmp = np.ascontiguousarray(K)
+    early = check(_cabi.lib().kmg_normalize_host(_ptr(tmp), n, max(n, 1))) == 1
+    K[...] = tmp
+    return early
+
+
+def center(K):
+    """center_K (kernels.py:387-395); returns a new array."""
+    K = np.ascontiguousarray(_square_f64(K, "center_K"))
+    n = K.shape[0]
+    out = np.empty_like(K)
+    check(_cabi.lib().kmg_center_host(_ptr(K), n, max(n, 1), _ptr(out), max(n, 1)))
+    return out
+
+
+def _ptr_array(mats):
+    mats = [np.ascontiguousarray(m, np.float64) for m in mats]
+    arr = (C.c_void_p * len(mats))(*[m.ctypes.data for m in mats])
+    return mats, arr
+
+
+def combine(kernels, u, degree=1, normalize=False):
+    """(sum_m u_m K_m) ** degree [+ normalize_K]  (ALIGNF.py:93; NLCKernels.py:52,97-99)."""
+    mats, arr = _ptr_array(kernels)
+    n = mats[0].shape[0]
+    for m in mats:
+        if m.shape != (n, n):
+            raise ValueError("combine: all kernels must be n x n")
+    u = np.ascontiguousarray(u, np.float64)
+    if u.size != len(mats):
+        raise ValueError("combine: one weight per kernel")
+    out = np.empty((n, n), np.float64)
+    check(_cabi.lib().kmg_combine_host(arr, len(mats), n, _ptr(u), int(degree), 1 if normalize else 0, _ptr(out)))
+    return out
+
+
+def alignf_stats(kernels, idx, y):
+    """ALIGNF Gram side (ALIGNF.py:28-29,36-58): returns (a, M) for the fit sub-block K[idx][:,idx]."""
+    mats, arr = _ptr_array(kernels)
+    n = mats[0].shape[0]
+    idx = np.ascontiguousarray(idx, np.int64)
+    y = np.ascontiguousarray(y, np.float64)
+    p = len(mats)
+    a = np.zeros(p)
+    M = np.zeros((p, p))
+    check(_cabi.lib().kmg_alignf_stats_host(arr, p, n, _ptr(idx), idx.size, _ptr(y), _ptr(a), _ptr(M)))
+    return a, M
+
+
+def nlck_grad(kernels_fit, u, alpha, degree):
+    """NLCK.grad (NLCKernels.py:61-66)."""
+    mats, arr = _ptr_array(kernels_fit)
+    nfit = mats[0].shape[0]
+    u = np.ascontiguousarray(u, np.float64)
+    alpha = np.ascontiguousarray(alpha, np.float64)
+    g = np.zeros(len(mats))
+    check(_cabi.lib().kmg_nlck_grad_host(arr, len(mats), nfit, _ptr(u), _ptr(alpha), int(degree), _ptr(g)))
+    return g
+
+
+def mismatch_table(k, m):
+    T = np.zeros(k + 1, np.int64)
+    check(_cabi.lib().kmg_mismatch_table_host(int(k), int(m), _ptr(T)))
+    return T

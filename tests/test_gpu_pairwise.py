@@ -1,0 +1,168 @@
+"""GPU parity: (k,m)-mismatch, weighted-degree and local-alignment kernels against the oracle and the
+reference's golden vectors.  Mismatch raw integers and WD fp64 values are bit-exact; local alignment
+(intended recursion, parity unpinned by the reference) is within 1e-12 relative."""
+import hashlib
+import re
+
+import numpy as np
+import pytest
+
+import oracle_c as oc
+import oracle_np as onp
+
+pytestmark = pytest.mark.gpu
+
+LA_RTOL = 1e-12  # BASELINE.json north_star: "within a stated relative tolerance (1e-12 in fp64)"
+
+
+@pytest.fixture(scope="module")
+def kd():
+    torch = pytest.importorskip("torch")
+    assert torch.cuda.is_available(), "these tests need a GPU"
+    from kmg import device
+    return device
+
+
+@pytest.fixture(scope="module")
+def kh():
+    from kmg import host
+    return host
+
+
+def _sha(K):
+    return hashlib.sha256(np.ascontiguousarray(K, np.float64).tobytes()).hexdigest()
+
+
+# ------------------------------------------------------------------------------------------ WD
+def test_wd_golden(kh, golden, dna):
+    codes, _ = dna
+    for name in [k for k in golden.files if k.startswith("wd_d") and "pair" not in k]:
+        d, n = map(int, re.match(r"wd_d(\d+)_n(\d+)", name).groups())
+        assert np.array_equal(kh.wd_gram(codes[:n], d), golden[name]), name
+    kat = dict(zip(golden["kat_names"].tolist(), golden["kat_sha256"].tolist()))
+    assert _sha(kh.wd_gram(codes[:256], 10)) == kat["wd_d10_Xtr0_256"]
+    assert _sha(kh.wd_gram(codes[:256], 5)) == kat["wd_d5_Xtr0_256"]
+    # identical pair off the diagonal gets the loop value, not the closed form (kernels.py:96 vs :74-81)
+    assert kh.wd_gram(codes[:1], 4, cols=codes[:1])[0, 0] == float(golden["wd_d4_pair00"]) == 99.00000000000001
+
+
+def test_wd_blocks_and_edges(kd, kh, dna):
+    codes, _ = dna
+    c = codes[:777]
+    want = oc.wd_block(c, c, 10)
+    planes = kd.pack(c, 0)
+    full = kd.wd_block(planes, planes, 101, 10, symmetric=True).cpu().numpy()
+    assert np.array_equal(full, want)
+    nosym = kd.wd_block(planes, planes, 101, 10).cpu().numpy()
+    assert np.array_equal(nosym, want)
+    blk = kd.wd_block(planes[100:333], planes, 101, 10, row_index0=100).cpu().numpy()
+    assert np.array_equal(blk, want[100:333])
+    # duplicates inside the data set (11 in Xtr0): off-diagonal identical pairs take the loop value
+    dup = np.concatenate((c[:5], c[:5]))
+    assert np.array_equal(kh.wd_gram(dup, 7), oc.wd_block(dup, dup, 7))
+    for L, d in ((2, 1), (33, 40), (64, 3), (128, 20)):
+        cc = onp.synthetic_codes(70, L, seed=L)
+        assert np.array_equal(kh.wd_gram(cc, d), oc.wd_block(cc, cc, d)), (L, d)
+    assert kh.wd_gram(codes[:0], 3).shape == (0, 0)
+    assert np.array_equal(kh.wd_gram(codes[:9], 5, cols=codes[20:51]), oc.wd_block(codes[:9], codes[20:51], 5, 0, 1 << 40))
+
+
+# ------------------------------------------------------------------------------------ mismatch
+@pytest.mark.parametrize("algo", [1, 2])
+def test_mismatch_golden(kh, golden, dna, algo):
+    codes, _ = dna
+    for name in [k for k in golden.files if k.startswith("mm_k")]:
+        k, m, n = map(int, re.match(r"mm_k(\d+)_m(\d+)_n(\d+)", name).groups())
+        K = kh.mismatch_gram(codes[:n], k, m, algo=algo)
+        assert np.array_equal(K, golden[name]), (name, algo)
+    kat = dict(zip(golden["kat_names"].tolist(), golden["kat_sha256"].tolist()))
+    assert _sha(kh.mismatch_gram(codes[:64], 4, 1, algo=algo)) == kat["mm_k4_m1_Xtr0_64"]
+
+
+def test_mismatch_pairwise_raw_vs_oracle(kd, kh, dna):
+    codes, _ = dna
+    c = codes[:150]
+    planes = kd.pack(c, 0)
+    for (k, m) in ((10, 1), (10, 2), (1, 0), (2, 1), (7, 3), (16, 1), (17, 2), (20, 0), (13, 3), (101, 1)):
+        want = oc.mismatch_raw_block(c, c, k, m)
+        got = kd.mismatch_block(planes, planes, 101, k, m, out_dtype=0).cpu().numpy()
+        assert np.array_equal(got.astype(np.int64), want), (k, m)
+        got = kd.mismatch_block(planes, planes, 101, k, m, out_dtype=1, symmetric=True).cpu().numpy()
+        assert np.array_equal(got, want.astype(np.float64)), (k, m, "sym")
+    # normalised, block rows, cross
+    sd = kd.mismatch_diag_sqrt(planes, 101, 10, 1)
+    raw = oc.mismatch_raw_block(c, c, 10, 1).astype(np.float64)
+    assert np.array_equal(sd.cpu().numpy(), np.sqrt(np.diag(raw)))
+    want = onp.normalize_K(raw.copy())
+    assert np.array_equal(kh.mismatch_gram(c, 10, 1), want)
+    blk = kd.mismatch_block(planes[33:77], planes, 101, 10, 1, row_index0=33, sd_rows=sd[33:77], sd_cols=sd).cpu().numpy()
+    assert np.array_equal(blk, want[33:77])
+    assert np.array_equal(kh.mismatch_gram(c[:10], 10, 1, cols=c[50:90], normalize=False), raw[:10, 50:90])
+    # other lengths
+    for L, k, m in ((12, 5, 1), (64, 9, 2), (128, 11, 1), (128, 8, 1)):
+        cc = onp.synthetic_codes(40, L, seed=L + k)
+        got = kh.mismatch_gram(cc, k, m, normalize=False, algo=1)
+        assert np.array_equal(got, oc.mismatch_raw_block(cc, cc, k, m).astype(np.float64)), (L, k, m)
+
+
+def test_mismatch_dense_vs_pairwise(kd, kh, dna):
+    """dense feature map + tcgen05 GEMM (the reference's own structure) == pairwise identity, k <= 8."""
+    codes, _ = dna
+    c = codes[2000:2300]
+    for (k, m) in ((5, 1), (6, 1), (6, 2), (8, 1), (4, 3), (3, 0)):
+        a = kh.mismatch_gram(c, k, m, normalize=False, algo=1)
+        b = kh.mismatch_gram(c, k, m, normalize=False, algo=2)
+        assert np.array_equal(a, b), (k, m)
+        a = kh.mismatch_gram(c, k, m, algo=1)
+        b = kh.mismatch_gram(c, k, m, algo=2)
+        assert np.array_equal(a, b), (k, m, "normalised")
+    phi = kh.mismatch_phi(c[:20], 4, 2)
+    assert np.array_equal(phi.astype(np.int64), onp.mismatch_phi(c[:20], 4, 2))
+    # MM(k,0) normalised == normalised spectrum
+    sp = onp.normalize_K(onp.spectrum_gram(c, 5))
+    assert np.array_equal(kh.mismatch_gram(c, 5, 0), sp)
+
+
+def test_mismatch_config2_subset(kh, dna):
+    """BASELINE config 2 shape: (k,m) = (10,1) over the challenge sequences (a 512-row sample here; the C oracle
+    needs ~20 s for it).  Normalised Gram bit-exact against the oracle."""
+    codes, _ = dna
+    idx = np.arange(0, 9000, 9000 // 512)[:512]
+    c = codes[idx]
+    want = onp.normalize_K(oc.mismatch_raw_block(c, c, 10, 1).astype(np.float64))
+    got = kh.mismatch_gram(c, 10, 1)
+    assert np.array_equal(got, want)
+    assert np.all(np.diag(got) == 1.0) and np.array_equal(got, got.T)
+
+
+# --------------------------------------------------------------------------- local alignment
+def test_la_affine_vs_oracle(kh, dna):
+    codes, _ = dna
+    c = codes[:24]
+    for (e, d, beta) in ((11, 1, 0.5), (-11, -1, 0.5), (11, 1, 0.1), (-5.5, -0.7, 1.3)):
+        want = oc.la_block(c, c, e, d, beta, 0)
+        got = kh.la_gram(c, e, d, beta, 0)
+        assert np.array_equal(got, got.T)
+        rel = np.abs(got - want).max() / np.abs(want).max()
+        assert rel <= LA_RTOL, (e, d, beta, rel)
+        assert np.all(np.abs(got - want) <= LA_RTOL * np.abs(want)), (e, d, beta)
+    v = kh.la_gram(codes[:1], -11, -1, 0.5, 0, cols=codes[1:2])[0, 0]
+    assert abs(v - 397.196) < 1e-3  # SURVEY.md A.5 probe
+
+
+def test_la_smith_and_shapes(kh, dna):
+    codes, _ = dna
+    c = codes[100:116]
+    for (e, d, beta) in ((11, 1, 0.5), (-11, -1, 0.5)):
+        want = oc.la_block(c, c, e, d, beta, 1)
+        got = kh.la_gram(c, e, d, beta, 1)
+        assert np.all(np.abs(got - want) <= LA_RTOL * np.abs(want) + 1e-300), (e, d, beta)
+    for L in (1, 5, 32, 33, 100, 128):
+        cc = onp.synthetic_codes(6, L, seed=L)
+        want = oc.la_block(cc, cc, -11, -1, 0.5, 0)
+        got = kh.la_gram(cc, -11, -1, 0.5, 0)
+        assert np.all(np.abs(got - want) <= LA_RTOL * np.abs(want) + 1e-300), L
+    # cross-Gram: x is always the row sequence
+    want = oc.la_block(c[:3], c[5:9], -11, -1, 0.5, 0, 0, 1 << 40)
+    got = kh.la_gram(c[:3], -11, -1, 0.5, 0, cols=c[5:9])
+    assert np.all(np.abs(got - want) <= LA_RTOL * np.abs(want))
