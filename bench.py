@@ -1,0 +1,361 @@
+#!/usr/bin/env python
+"""
+bench.py -- Gram entries/sec for the B200-native Gram construction (contract: see the task statement).
+
+Headline workload (BASELINE.json configs[2]): sum of spectrum kernels k=1..7 over n = 200 000 synthetic
+uniform-random 101-bp sequences (PCG64 seed 3), Gram block-rows sharded over the GPUs.  The n x n fp64 Gram
+(320 GB) does not fit one GPU, so the unit of work is ONE BLOCK-ROW of 25 000 x 200 000 entries per GPU
+(weak scaling: at --gpus 8 the ranks together build the complete 200k x 200k Gram; at --gpus N < 8 they
+build its first N block-rows).  Every rank holds all packed sequences (6.4 MB) and builds its own int8
+feature matrix Phi (4.4 GB) locally: no collective on the data path.
+
+A "step" = spectrum_phi (packed sequences -> Phi, all 200k rows) + the tcgen05 int8 Gram GEMM of the
+rank's block-row with the fp64 epilogue, inputs (packed sequences) resident in HBM.  Phi (4.4 GB) and the
+40 GB output are far larger than the 126 MB L2, so no L2 flush is needed between iterations.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
+  python bench.py --impl reference ...                          # the CPU restatement on the host cores
+
+One JSON line on stdout (rank 0).  Extra keys beyond the contract: "roofline", "cpu_baseline", "kernels"
+(device-resident numbers for the other BASELINE configs at N=1), "clocks".
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (os.path.join(ROOT, "kernel-methods-for-genomics_b200"), os.path.join(ROOT, "oracle")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+N_SEQ = 200_000
+ROWS_PER_GPU = 25_000
+L = 101
+KS = list(range(1, 8))
+D_ALG = sum(4 ** k for k in KS)  # 21 844 algorithmic feature width (padding to 21 888 is not counted)
+SEED = 3
+NOMINAL_INT8_TOPS = 4500.0
+NOMINAL_HBM_GBS = 7700.0
+
+
+def synthetic_codes(n, seed):
+    rng = np.random.Generator(np.random.PCG64(seed))
+    return rng.integers(0, 4, size=(n, L), dtype=np.uint8)
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"hbm_gbs": float(p["hbm_gbs"]), "bf16_burst": float(p["bf16_tflops"]),
+                "bf16_sustained": float(p.get("bf16_tflops_sustained", p["bf16_tflops"])), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_burst": 1590.0, "bf16_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------------------------------
+# reference arm / cpu_baseline: the plain-C restatement of the reference's algorithm (oracle/kmg_oracle.c,
+# dense Phi + dot products as kernels.py:12-47 does) on all host threads, on a bounded sample of the workload
+# ----------------------------------------------------------------------------------------------------
+def cpu_sample_shape(budget_s, oc):
+    """rows x cols of the block-row the CPU can do in ~budget_s seconds (calibrated on a tiny sample)."""
+    codes = synthetic_codes(1024, SEED)
+    t0 = time.perf_counter()
+    oc.spectrum_block(codes[:16], codes[:256], KS)
+    rate = 16 * 256 / max(time.perf_counter() - t0, 1e-6)  # entries/s incl. feature build (pessimistic)
+    cols = 4096
+    rows = int(max(16, min(1024, budget_s * rate * 2 / cols)))
+    return rows, cols
+
+
+def run_cpu(rows, cols, steps, warmup, oc):
+    codes = synthetic_codes(max(rows, cols), SEED)
+    r, c = codes[:rows], codes[:cols]
+    for _ in range(warmup):
+        oc.spectrum_block(r, c, KS)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        oc.spectrum_block(r, c, KS)
+    dt = (time.perf_counter() - t0) / steps
+    return rows * cols / dt, dt
+
+
+def reference_arm(args, rank):
+    if rank != 0:
+        return
+    import oracle_c as oc
+    oc.build()
+    threads = oc.num_threads()
+    rows, cols = cpu_sample_shape(2.0, oc)
+    value, dt = run_cpu(rows, cols, args.steps, args.warmup, oc)
+    sample = f"{rows} x {cols} entries of the block-row per step (k=1..7 dense Phi + dot products, oracle/kmg_oracle.c)"
+    line = {
+        "impl": "reference", "metric": "gram_entries_per_sec", "value": value, "unit": "entries/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "s8->s32->f64", "data": "synthetic",
+        "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": value, "unit": "entries/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "entries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "the reference is single-threaded pure Python (2.5e4 entries/s on config 1, BASELINE.md) and cannot travel to the GPU box; "
+                "this arm times its algorithm restated in C on all host threads",
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(n_gpus):
+    return {"workload": "BASELINE configs[2]: sum of spectrum kernels k=1..7, n=200000 synthetic 101-bp sequences (PCG64 seed 3), "
+                        "one 25000 x 200000 fp64 Gram block-row per GPU",
+            "n": N_SEQ, "rows_per_gpu": ROWS_PER_GPU, "block_rows_built": n_gpus, "L": L, "ks": KS, "feature_width": D_ALG,
+            "output": "fp64 (exact integers)", "sharding": f"block-row x{n_gpus}, no data-path collective",
+            "l2": "inputs (Phi 4.4 GB) and output (40 GB) exceed the 126 MB L2; no flush needed"}
+
+
+# ----------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-extras", action="store_true", help="skip the per-kernel numbers for the other BASELINE configs")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--n", type=int, default=N_SEQ, help="(debug) number of sequences")
+    ap.add_argument("--rows", type=int, default=ROWS_PER_GPU, help="(debug) rows per GPU")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        reference_arm(args, rank)
+        return
+
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from kmg import device as kd
+    from kmg import host as kh
+    from kmg._cabi import lib
+    lib()
+
+    n, R = args.n, args.rows
+    peaks = load_peaks()
+    codes = synthetic_codes(n, SEED)
+    planes = kd.pack(codes, 0)  # every rank holds all packed sequences
+    W = kd.phi_width(KS)
+    phi = torch.empty((n, W), dtype=torch.int8, device="cuda")
+    row0 = (rank * R) % max(n - R + 1, 1)
+    out = torch.empty((R, n), dtype=torch.float64, device="cuda")
+
+    def step():
+        kd.spectrum_phi(planes, L, KS, out=phi)
+        kd.gram_i8(phi[row0:row0 + R], phi, row_index0=row0, col_index0=0, out_dtype=1, m_sub=2, out=out)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * args.steps + 2)]
+    ev[0].record()
+    gemm_ms = []
+    for i in range(args.steps):
+        kd.spectrum_phi(planes, L, KS, out=phi)
+        ev[2 * i + 1].record()
+        kd.gram_i8(phi[row0:row0 + R], phi, row_index0=row0, col_index0=0, out_dtype=1, m_sub=2, out=out)
+        ev[2 * i + 2].record()
+    ev[-1].record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = ev[0].elapsed_time(ev[-1])
+    gemm_ms = [ev[2 * i + 1].elapsed_time(ev[2 * i + 2]) for i in range(args.steps)]
+    t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    entries_per_step = float(R) * n * world
+    value = entries_per_step / (ms_per_step * 1e-3)
+
+    # ---- roofline of the dominant kernel (gram_i8_tcgen05_kernel<2>): tensor bound
+    gemm_avg_ms = float(np.mean(gemm_ms))
+    alg_ops = 2.0 * D_ALG * R * n  # 2*D ops per delivered entry, one launch = one block-row
+    achieved_tops = alg_ops / (gemm_avg_ms * 1e-3) / 1e12
+    peak_tops = 2.0 * peaks["bf16_sustained"]
+    roofline = {
+        "kernel": "gram_i8_tcgen05_kernel<M_SUB=2>", "bound": "tensor", "achieved": achieved_tops, "peak": peak_tops,
+        "unit": "TOP/s (int8)", "frac": achieved_tops / peak_tops,
+        "peak_source": f"2 x bf16_tflops_sustained of MEASURED_PEAKS.json ({peaks['source']}): the file has no int8 entry and the "
+                       "tcgen05 kind::i8 rate is twice kind::f16; a cuBLAS bf16 denominator doubled, so a tight int8 kernel can read above 1.0",
+        "frac_of_nominal_int8_4500": achieved_tops / NOMINAL_INT8_TOPS,
+        "algorithmic_ops_per_launch": alg_ops, "kernel_ms": gemm_avg_ms, "kernel_share_of_step": gemm_avg_ms / ms_per_step,
+        "traffic": TRAFFIC_BYTES_PER_LAUNCH,
+        "hbm_write_gbs": 8.0 * R * n / (gemm_avg_ms * 1e-3) / 1e9,
+    }
+
+    # ---- end to end through the reference-facing C-ABI with host buffers (kmg_spectrum_host)
+    e2e_rows = min(2048, R)
+    rows_h = np.ascontiguousarray(codes[row0:row0 + e2e_rows])
+    kh.spectrum_gram(rows_h[:256], KS, cols=codes)  # warm the path (allocations, tile list)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = 3
+    for _ in range(e2e_steps):
+        Kh = kh.spectrum_gram(rows_h, KS, cols=codes)
+    dt = (time.perf_counter() - t0) / e2e_steps
+    te = torch.tensor([dt], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e = {"value": e2e_rows * float(n) * world / float(te.item()), "unit": "entries/s",
+           "h2d_bytes_per_step": int((e2e_rows + n) * L), "d2h_bytes_per_step": int(e2e_rows * n * 8),
+           "sample": f"{e2e_rows} x {n} rows of the block-row per GPU per call through kmg_spectrum_host (numpy in, numpy fp64 out; "
+                     "pageable host memory; H2D of the sequences and D2H of the Gram inside the timed region)",
+           "checksum": float(Kh[0, :8].sum())}
+    del Kh
+
+    line = {
+        "metric": "gram_entries_per_sec", "value": value, "unit": "entries/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "s8->s32->f64", "data": "synthetic", "config": workload_config(world), "e2e": e2e,
+        "gpu_launches": 2 * args.steps, "roofline": roofline, "clocks": clocks,
+    }
+
+    if rank == 0 and world == 1 and not args.no_extras:
+        del out
+        torch.cuda.empty_cache()
+        line["kernels"] = extras(kd, torch, codes, planes, phi, peaks)
+    if rank == 0 and world == 1 and not args.no_cpu:
+        import oracle_c as oc
+        oc.build()
+        rows, cols = cpu_sample_shape(4.0, oc)
+        v, dtc = run_cpu(rows, cols, 3, 1, oc)
+        line["cpu_baseline"] = {"value": v, "unit": "entries/s", "cores": oc.num_threads(), "kind": "port",
+                                "sample": f"{rows} x {cols} entries of the block-row, 3 timed passes of {dtc:.1f} s (oracle/kmg_oracle.c: "
+                                          "dense Phi + dot products as kernels.py:12-47, all host threads)"}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel, from the ncu --set full
+# capture summarised under profiles/ (null until a capture of this exact launch exists)
+TRAFFIC_BYTES_PER_LAUNCH = None
+
+
+def extras(kd, torch, codes, planes, phi, peaks):
+    """Device-resident numbers for the other BASELINE configs (N=1 only): each timed with CUDA events over 3 launches."""
+    def timed(fn, iters=3):
+        fn(); torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(iters):
+            fn()
+        b.record(); torch.cuda.synchronize()
+        return a.elapsed_time(b) / iters
+
+    res = {}
+    hbm = peaks["hbm_gbs"]
+    # spectrum k=6 (configs[0] kernel at scale): 32768 x 32768 block, symmetric, fp64
+    n6 = 32768
+    phi6 = kd.spectrum_phi(planes[:n6], L, [6])
+    out = torch.empty((n6, n6), dtype=torch.float64, device="cuda")
+    ms = timed(lambda: kd.gram_i8(phi6, phi6, out_dtype=1, symmetric=True, out=out))
+    res["spectrum_k6_sym_32768"] = {"entries_per_s": n6 * n6 / ms * 1e3, "ms": ms, "hbm_write_gbs": n6 * n6 * 8 / ms / 1e6,
+                                    "frac_hbm_write": n6 * n6 * 8 / ms / 1e6 / hbm}
+    del out, phi6
+    # configs[1]: (k,m)=(10,1) mismatch over 9000 sequences, symmetric, normalised fp64 (pairwise bit-vector kernel)
+    n2 = 9000
+    sd = kd.mismatch_diag_sqrt(planes[:n2], L, 10, 1)
+    out = torch.empty((n2, n2), dtype=torch.float64, device="cuda")
+    ms = timed(lambda: kd.mismatch_block(planes[:n2], planes[:n2], L, 10, 1, symmetric=True, sd_rows=sd, sd_cols=sd, out=out))
+    res["mismatch_k10_m1_sym_9000"] = {"entries_per_s": n2 * n2 / ms * 1e3, "ms": ms,
+                                       "window_pair_tests_per_s": (n2 * (n2 + 1) / 2) * 92 * 92 / ms * 1e3}
+    del out
+    # configs[3]: weighted degree d=10, 100k sequences: one 12500 x 100000 block-row
+    n3, r3 = 100_000, 12_500
+    out = torch.empty((r3, n3), dtype=torch.float64, device="cuda")
+    ms = timed(lambda: kd.wd_block(planes[:r3], planes[:n3], L, 10, out=out))
+    res["wd_d10_blockrow_12500x100000"] = {"entries_per_s": r3 * n3 / ms * 1e3, "ms": ms, "hbm_write_gbs": r3 * n3 * 8 / ms / 1e6,
+                                           "frac_hbm_write": r3 * n3 * 8 / ms / 1e6 / hbm}
+    del out
+    # configs[4]: local alignment (intended recursion), 20k sequences: one 1024 x 20000 block
+    n4, r4 = 20_000, 1024
+    out = torch.empty((r4, n4), dtype=torch.float64, device="cuda")
+    ms = timed(lambda: kd.la_block(planes[:r4], planes[:n4], L, 11, 1, 0.5, 0, out=out), iters=1)
+    res["la_affine_block_1024x20000"] = {"entries_per_s": r4 * n4 / ms * 1e3, "ms": ms, "dp_cells_per_s": r4 * n4 * 10201 / ms * 1e3}
+    return res
+
+
+if __name__ == "__main__":
+    main()

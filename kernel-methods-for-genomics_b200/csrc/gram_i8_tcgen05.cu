@@ -19,6 +19,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include <map>
 #include <mutex>
@@ -51,6 +52,8 @@ struct KernelParams {
     const double* sd_rows;  // sqrt(diag) per local row / col for cosine normalisation; null = raw
     const double* sd_cols;
     const int4* tiles;  // {row_tile, col_tile, mirror, 0}
+    uint32_t* wave_counter;  // grid-wide arrival counter (zeroed before the launch) or null
+    uint64_t hint_a, hint_b;  // L2 eviction policy of the A / B operand loads
 };
 
 template <int M_SUB>
@@ -62,68 +65,72 @@ struct Cfg {
     static constexpr uint32_t A_BYTES = BM * BK;
     static constexpr uint32_t B_BYTES = BN * BK;
     static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr uint32_t EPI_STAGE_WORDS = 32 * 33;  // per epilogue warp: 32 x 32 int32 transpose tile, padded
+    static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + NUM_EPI_WARPS * EPI_STAGE_WORDS * 4;
 };
 
-__device__ __forceinline__ void store_chunk(const KernelParams& p, const uint32_t (&v)[32], int64_t row, int64_t col0,
-                                            bool mirror) {
-    // thread owns row `row`, 32 consecutive columns starting at col0 (local block coordinates)
-    if (row >= p.rows) return;
-    const int64_t ncol = (p.cols - col0 < 32) ? (p.cols - col0) : 32;
-    if (ncol <= 0) return;
-    const int64_t grow = p.row_index0 + row;
+// Epilogue store of one 32-row x 32-column accumulator chunk.  After tcgen05.ld thread t holds row t, so a
+// direct store would touch 32 different cache lines per instruction (measured: the LSU wavefronts of that pattern
+// cost ~17 us per 256x256 tile).  Instead the chunk is transposed through a per-warp shared-memory tile
+// (row stride 33 words: conflict-free both ways) and every warp store writes 32 consecutive entries of one row.
+// The mirrored store K[c][r] needs no transpose: for a fixed register j the 32 lanes are 32 consecutive rows.
+__device__ __forceinline__ void store_chunk(const KernelParams& p, const uint32_t (&v)[32], uint32_t* stage /*[32][33]*/,
+                                            int lane, int64_t row_base, int64_t col0, bool mirror) {
+    const int64_t ncol = (p.cols - col0 < 32) ? (p.cols - col0) : 32;  // warp-uniform, > 0
+    const int64_t row_t = row_base + lane;                             // the row this thread holds in registers
+    const int64_t col = col0 + lane;                                   // the column this thread stores
+    const bool col_ok = lane < ncol;
+    int64_t nrow = p.rows - row_base;
+    if (nrow > 32) nrow = 32;
+    if (nrow <= 0) return;  // warp-uniform
+#pragma unroll
+    for (int j = 0; j < 32; ++j) stage[lane * 33 + j] = v[j];
+    __syncwarp();
     if (p.out_dtype == KMG_OUT_S32) {
-        int32_t* dst = reinterpret_cast<int32_t*>(p.out) + row * p.ldo + col0;
-        if (ncol == 32 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4)
-                *reinterpret_cast<int4*>(dst + j) = make_int4((int)v[j], (int)v[j + 1], (int)v[j + 2], (int)v[j + 3]);
-        } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-                if (j < ncol) dst[j] = (int32_t)v[j];
+        int32_t* dst = reinterpret_cast<int32_t*>(p.out) + row_base * p.ldo + col;
+        if (col_ok) {
+#pragma unroll 8
+            for (int rr = 0; rr < 32; ++rr)
+                if (rr < nrow) dst[(int64_t)rr * p.ldo] = (int32_t)stage[rr * 33 + lane];
         }
-        if (mirror) {
-            int32_t* dt = reinterpret_cast<int32_t*>(p.out_t) + col0 * p.ldo_t + row;
+        if (mirror && row_t < p.rows) {
+            int32_t* dt = reinterpret_cast<int32_t*>(p.out_t) + col0 * p.ldo_t + row_t;
 #pragma unroll
             for (int j = 0; j < 32; ++j)
                 if (j < ncol) dt[(int64_t)j * p.ldo_t] = (int32_t)v[j];
         }
-        return;
-    }
-    double w[32];
-    if (p.sd_rows != nullptr) {
-        // normalize_K (kernels.py:408-414): K_ij / (sqrt(K_ii) * sqrt(K_jj)), diagonal := 1.0
-        const double sr = p.sd_rows[row];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            double val = 0.0;
-            if (j < ncol) {
-                const double den = __dmul_rn(sr, p.sd_cols[col0 + j]);
-                val = __ddiv_rn((double)(int32_t)v[j], den);
-                if (grow == p.col_index0 + col0 + j) val = 1.0;
+    } else {
+        double* dst = reinterpret_cast<double*>(p.out) + row_base * p.ldo + col;
+        const bool norm = p.sd_rows != nullptr;
+        const double sc = (norm && col_ok) ? p.sd_cols[col] : 1.0;
+        if (col_ok) {
+#pragma unroll 8
+            for (int rr = 0; rr < 32; ++rr) {
+                if (rr < nrow) {
+                    double val = (double)(int32_t)stage[rr * 33 + lane];
+                    if (norm) {
+                        // normalize_K (kernels.py:408-414): K_ij / (sqrt(K_ii) * sqrt(K_jj)), diagonal := 1.0
+                        val = __ddiv_rn(val, __dmul_rn(p.sd_rows[row_base + rr], sc));
+                        if (p.row_index0 + row_base + rr == p.col_index0 + col) val = 1.0;
+                    }
+                    dst[(int64_t)rr * p.ldo] = val;
+                }
             }
-            w[j] = val;
         }
-    } else {
+        if (mirror && row_t < p.rows) {
+            double* dt = reinterpret_cast<double*>(p.out_t) + col0 * p.ldo_t + row_t;
+            const double sr = norm ? p.sd_rows[row_t] : 1.0;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) w[j] = (double)(int32_t)v[j];
+            for (int j = 0; j < 32; ++j) {
+                if (j < ncol) {
+                    double val = (double)(int32_t)v[j];
+                    if (norm) val = __ddiv_rn(val, __dmul_rn(sr, p.sd_cols[col0 + j]));  // mirrored tiles never contain the diagonal
+                    dt[(int64_t)j * p.ldo_t] = val;
+                }
+            }
+        }
     }
-    double* dst = reinterpret_cast<double*>(p.out) + row * p.ldo + col0;
-    if (ncol == 32 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
-#pragma unroll
-        for (int j = 0; j < 32; j += 2) *reinterpret_cast<double2*>(dst + j) = make_double2(w[j], w[j + 1]);
-    } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-            if (j < ncol) dst[j] = w[j];
-    }
-    if (mirror) {
-        double* dt = reinterpret_cast<double*>(p.out_t) + col0 * p.ldo_t + row;
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-            if (j < ncol) dt[(int64_t)j * p.ldo_t] = w[j];
-    }
+    __syncwarp();  // the staging tile is reused by the next chunk
 }
 
 template <int M_SUB>
@@ -138,6 +145,7 @@ gram_i8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     uint64_t* tfull = empty + C::STAGES;
     uint64_t* tempty = tfull + C::ACC_STAGES;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + C::ACC_STAGES);
+    uint32_t* epi_stage = reinterpret_cast<uint32_t*>(smem + C::STAGES * C::STAGE_BYTES + 256);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -169,16 +177,32 @@ gram_i8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     if (warp == 0) {
         // ------------------------------------------------------------ TMA producer
         if (lane == 0) {
-            uint32_t stage = 0, phase = 0;
-            for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
+            uint32_t stage = 0, phase = 0, wave = 0;
+            for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x, ++wave) {
                 const int4 tile = p.tiles[t];
                 const int32_t row0 = tile.x * C::BM, col0 = tile.y * BN;
+                if (p.wave_counter != nullptr) {
+                    // Wave barrier: all CTAs start their w-th tile together.  The 148 tiles of a wave share A/B
+                    // panels (band rasterisation); without this the CTAs drift apart over hundreds of waves, the
+                    // k-slabs they share leave L2 before the partner arrives and every panel is fetched from HBM
+                    // by each CTA separately (measured: 275 GB of DRAM reads per launch instead of ~80 GB).
+                    ptx::red_release_gpu_add(p.wave_counter, 1u);
+                    const uint32_t done = (wave + 1) * gridDim.x;
+                    const uint32_t target = done < (uint32_t)p.ntiles ? done : (uint32_t)p.ntiles;
+                    if (ptx::ld_acquire_gpu(p.wave_counter) < target) {
+                        const uint64_t t0 = ptx::globaltimer_ns();
+                        while (ptx::ld_acquire_gpu(p.wave_counter) < target) {
+                            __nanosleep(200);
+                            if (ptx::globaltimer_ns() - t0 > 4000000000ull) __trap();
+                        }
+                    }
+                }
                 for (int kb = 0; kb < p.kblocks; ++kb) {
                     ptx::mbar_wait(&empty[stage], phase ^ 1);
                     ptx::mbar_arrive_expect_tx(&full[stage], C::STAGE_BYTES);
                     uint8_t* sa = smem + stage * C::STAGE_BYTES;
-                    ptx::tma_load_2d(sa, &tmA, &full[stage], kb * BK, row0);
-                    ptx::tma_load_2d(sa + C::A_BYTES, &tmB, &full[stage], kb * BK, col0);
+                    ptx::tma_load_2d_hint(sa, &tmA, &full[stage], kb * BK, row0, p.hint_a);
+                    ptx::tma_load_2d_hint(sa + C::A_BYTES, &tmB, &full[stage], kb * BK, col0, p.hint_b);
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -227,7 +251,7 @@ gram_i8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             ptx::tcgen05_fence_after();
 #pragma unroll
             for (int ms = 0; ms < M_SUB; ++ms) {
-                const int64_t row = (int64_t)tile.x * C::BM + ms * 128 + quarter * 32 + lane;
+                const int64_t row_base = (int64_t)tile.x * C::BM + ms * 128 + quarter * 32;
 #pragma unroll 1
                 for (int ch = 0; ch < 4; ++ch) {
                     const int64_t col0 = (int64_t)tile.y * BN + half * 128 + ch * 32;
@@ -237,7 +261,7 @@ gram_i8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                     uint32_t v[32];
                     ptx::tmem_ld_32x32b_x32(taddr, v);
                     ptx::tmem_ld_wait();
-                    store_chunk(p, v, row, col0, mirror);
+                    store_chunk(p, v, epi_stage + (warp - 4) * C::EPI_STAGE_WORDS, lane, row_base, col0, mirror);
                 }
             }
             ptx::tcgen05_fence_before();
@@ -309,11 +333,31 @@ int make_map(CUtensorMap* m, const int8_t* base, int64_t nrows, int64_t Dpad, in
 // transposed image is not covered by a computed tile.
 struct TileKey {
     int64_t rows, cols, r0, c0;
-    int bm, sym;
+    int bm, sym, band;
     bool operator<(const TileKey& o) const {
-        return std::tie(rows, cols, r0, c0, bm, sym) < std::tie(o.rows, o.cols, o.r0, o.c0, o.bm, o.sym);
+        return std::tie(rows, cols, r0, c0, bm, sym, band) < std::tie(o.rows, o.cols, o.r0, o.c0, o.bm, o.sym, o.band);
     }
 };
+
+int env_int(const char* name, int dflt) {
+    const char* v = getenv(name);
+    return v ? atoi(v) : dflt;
+}
+
+// rotating pool of zero-initialised arrival counters, one per launch in flight
+constexpr int COUNTER_SLOTS = 1024;
+uint32_t* g_counters[64] = {};
+unsigned g_counter_next[64] = {};
+int get_counter(cudaStream_t stream, uint32_t** out) {
+    int dev = 0;
+    KMG_CUDA_CHECK(cudaGetDevice(&dev));
+    dev &= 63;
+    if (g_counters[dev] == nullptr) KMG_CUDA_CHECK(cudaMalloc(&g_counters[dev], COUNTER_SLOTS * sizeof(uint32_t)));
+    uint32_t* c = g_counters[dev] + (g_counter_next[dev]++ % COUNTER_SLOTS);
+    KMG_CUDA_CHECK(cudaMemsetAsync(c, 0, sizeof(uint32_t), stream));
+    *out = c;
+    return KMG_OK;
+}
 struct TileList {
     int4* dev = nullptr;
     int32_t n = 0;
@@ -330,7 +374,7 @@ int get_tiles(const TileKey& key, cudaStream_t stream, TileList* out) {
     if (it != g_tile_cache.end()) { *out = it->second; return KMG_OK; }
     const int BM = key.bm;
     const int64_t tm_n = (key.rows + BM - 1) / BM, tn_n = (key.cols + BN - 1) / BN;
-    const int G = 8;
+    const int G = key.band;
     std::vector<int4> tiles;
     tiles.reserve((size_t)(tm_n * tn_n));
     int64_t entries = 0;
@@ -409,7 +453,10 @@ int kmg_gram_i8_launch(const GramI8Args* a, cudaStream_t stream) {
     rc = make_map(&tmB, a->phi_cols, a->cols, a->Dpad, a->ld_phi, BN);
     if (rc) return rc;
 
-    TileKey key{a->rows, a->cols, a->row_index0, a->col_index0, BM, a->symmetric ? 1 : 0};
+    static const int band = env_int("KMG_GEMM_BAND", 8);
+    static const int sync_waves = env_int("KMG_GEMM_SYNC", 1);
+    static const int hint_mode = env_int("KMG_GEMM_HINT", 0);
+    TileKey key{a->rows, a->cols, a->row_index0, a->col_index0, BM, a->symmetric ? 1 : 0, band > 0 ? band : 8};
     TileList tl;
     rc = get_tiles(key, stream, &tl);
     if (rc) return rc;
@@ -426,6 +473,13 @@ int kmg_gram_i8_launch(const GramI8Args* a, cudaStream_t stream) {
     p.out_t = a->symmetric ? a->out_t : nullptr; p.ldo_t = a->ldo_t;
     p.sd_rows = a->sd_rows; p.sd_cols = a->sd_cols;
     p.tiles = tl.dev;
+    p.wave_counter = nullptr;
+    if (sync_waves && tl.n > sms) {
+        rc = get_counter(stream, &p.wave_counter);
+        if (rc) return rc;
+    }
+    p.hint_a = hint_mode == 1 ? ptx::L2_EVICT_LAST : ptx::L2_EVICT_NORMAL;
+    p.hint_b = hint_mode == 2 ? ptx::L2_EVICT_FIRST : ptx::L2_EVICT_NORMAL;
     return m_sub == 1 ? launch<1>(tmA, tmB, p, sms, stream) : launch<2>(tmA, tmB, p, sms, stream);
 }
 
