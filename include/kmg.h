@@ -127,6 +127,13 @@ int kmg_la_dev(const uint32_t* d_planes_rows, const uint32_t* d_planes_cols, int
 int kmg_normalize_dev(double* d_K, int64_t n, int64_t ld, double* d_sd_scratch /* n */, void* stream);
 int64_t kmg_center_workspace_bytes(int64_t n);
 int kmg_center_dev(const double* d_K, int64_t n, int64_t ld, double* d_out, int64_t ldo, void* d_workspace, void* stream);
+/* pieces of center_K for a block-row sharded Gram (kmg/dist.py all-reduces the column sums and the grand sum):
+ * out = K - cs[j]/n - rs[i]/n + g/n^2 with rs = row sums of the block, cs = column sums over ALL n rows, g = grand sum. */
+int kmg_row_sums_dev(const double* d_K, int64_t rows, int64_t cols, int64_t ld, double* d_rs, void* stream);
+int64_t kmg_col_sums_workspace_bytes(int64_t rows, int64_t cols);
+int kmg_col_sums_dev(const double* d_K, int64_t rows, int64_t cols, int64_t ld, double* d_cs, void* d_workspace, void* stream);
+int kmg_center_apply_dev(const double* d_K, int64_t rows, int64_t cols, int64_t n_total, int64_t ld, const double* d_rs,
+                         const double* d_cs, const double* d_g, double* d_out, int64_t ldo, void* stream);
 int kmg_gather_dev(const double* d_K, int64_t ld, const int64_t* d_idx, int64_t m, double* d_out, int64_t ldo, void* stream);
 int kmg_combine_dev(const double* const* d_Ks /* host array of device pointers */, const int64_t* lds, const double* u, int p,
                     int degree, int64_t rows, int64_t cols, double* d_out, int64_t ldo, void* stream);

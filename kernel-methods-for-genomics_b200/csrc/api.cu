@@ -8,6 +8,10 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
+#include <future>
+#include <map>
+#include <mutex>
 #include <vector>
 
 #include "../../include/kmg.h"
@@ -29,20 +33,75 @@ void kmg_set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
+// KMG_TRACE=1: phase timings of the host entry points on stderr
+static void kmg_trace(const char* what) {
+    static const bool on = getenv("KMG_TRACE") != nullptr;
+    if (!on) return;
+    static thread_local std::chrono::steady_clock::time_point last = std::chrono::steady_clock::now();
+    const auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "[kmg] %-48s +%.3f ms\n", what, std::chrono::duration<double, std::milli>(now - last).count());
+    last = now;
+}
+
 namespace {
+
+// Size-bucketed cache of device allocations: cudaMalloc / cudaFree of multi-GB buffers cost tens of
+// milliseconds per host call (cudaFree also synchronises the device); repeated Gram builds (run.py
+// builds nine kernels) reuse the buffers instead.  kmg_release() returns everything to the driver.
+struct DevCache {
+    std::mutex mu;
+    std::multimap<std::pair<int, size_t>, void*> free_list;  // (device, bucket bytes) -> pointer
+    size_t cached_bytes = 0;
+    static size_t bucket(size_t n) {
+        size_t b = 256;
+        while (b < n) b <<= 1;
+        const size_t step = b >> 3;  // 8 sub-buckets per power of two: <= 12.5 % slack
+        return step ? (n + step - 1) / step * step : b;
+    }
+    void flush() {
+        for (auto& kv : free_list) { cudaSetDevice(kv.first.first); cudaFree(kv.second); }
+        free_list.clear();
+        cached_bytes = 0;
+    }
+};
+DevCache g_cache;
 
 struct DevBuf {
     void* p = nullptr;
-    size_t bytes = 0;
-    ~DevBuf() { if (p) cudaFree(p); }
+    size_t bytes = 0;  // bucket size actually allocated
+    int dev = 0;
+    ~DevBuf() { release(); }
+    void release() {
+        if (!p) return;
+        std::lock_guard<std::mutex> lk(g_cache.mu);
+        g_cache.free_list.emplace(std::make_pair(dev, bytes), p);
+        g_cache.cached_bytes += bytes;
+        p = nullptr;
+    }
     int alloc(size_t n) {
-        if (p) { cudaFree(p); p = nullptr; }
-        bytes = n;
+        release();
         if (n == 0) return KMG_OK;
-        cudaError_t e = cudaMalloc(&p, n);
+        cudaGetDevice(&dev);
+        bytes = DevCache::bucket(n);
+        {
+            std::lock_guard<std::mutex> lk(g_cache.mu);
+            auto it = g_cache.free_list.find(std::make_pair(dev, bytes));
+            if (it != g_cache.free_list.end()) {
+                p = it->second;
+                g_cache.free_list.erase(it);
+                g_cache.cached_bytes -= bytes;
+                return KMG_OK;
+            }
+        }
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e != cudaSuccess) {  // give the cached buffers back and retry once
+            cudaGetLastError();
+            { std::lock_guard<std::mutex> lk(g_cache.mu); g_cache.flush(); cudaSetDevice(dev); }
+            e = cudaMalloc(&p, bytes);
+        }
         if (e != cudaSuccess) {
             p = nullptr;
-            kmg_set_error("cudaMalloc(%zu bytes) failed: %s", n, cudaGetErrorString(e));
+            kmg_set_error("cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
             cudaGetLastError();
             return KMG_ERR_NOMEM;
         }
@@ -103,12 +162,80 @@ int upload_planes(const uint8_t* seqs, int64_t n, int L, int fmt, DevBuf* planes
 int pick_block_rows(int64_t nr, int64_t nc, int64_t* block_rows) {
     size_t free_b = 0, total_b = 0;
     KMG_CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
+    { std::lock_guard<std::mutex> lk(g_cache.mu); free_b += g_cache.cached_bytes; }  // cached buffers are reclaimable
     const double budget = 0.70 * (double)free_b;
     int64_t r = (int64_t)(budget / (2.0 * 8.0 * (double)std::max<int64_t>(nc, 1)));
     r = std::min<int64_t>(r, 32768);
     r = (r / 256) * 256;
     KMG_REQUIRE(r >= 256 || r >= nr, KMG_ERR_NOMEM, "not enough device memory for a 256-row block of %lld columns", (long long)nc);
     *block_rows = std::max<int64_t>(std::min<int64_t>(r, nr), 1);
+    return KMG_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// Device -> pageable host copy through a ring of pinned staging slots.  A plain cudaMemcpy into
+// pageable memory is staged by the driver on one thread (3-4 GB/s measured into freshly
+// allocated numpy memory); here the DMA into pinned slots runs at PCIe speed while one host
+// thread per slot copies (and first-touches) the caller's pages in parallel.
+// ------------------------------------------------------------------------------------------
+constexpr int D2H_SLOTS = 16;
+constexpr size_t D2H_SLOT_BYTES = 8u << 20;
+struct PinnedRing {
+    void* buf[D2H_SLOTS] = {};
+    cudaEvent_t ev[D2H_SLOTS] = {};
+    bool ready = false;
+    std::mutex mu;
+};
+PinnedRing g_ring;
+
+int ring_init() {
+    if (g_ring.ready) return KMG_OK;
+    for (int i = 0; i < D2H_SLOTS; ++i) {
+        KMG_CUDA_CHECK(cudaHostAlloc(&g_ring.buf[i], D2H_SLOT_BYTES, cudaHostAllocDefault));
+        KMG_CUDA_CHECK(cudaEventCreateWithFlags(&g_ring.ev[i], cudaEventDisableTiming));
+    }
+    g_ring.ready = true;
+    return KMG_OK;
+}
+
+// src: device, `rows` x `cols` doubles, contiguous.  dst: host, row stride ldk.
+int d2h_rows(double* dst, int64_t ldk, const double* src, int64_t cols, int64_t rows, cudaStream_t s) {
+    if (rows <= 0 || cols <= 0) return KMG_OK;
+    std::lock_guard<std::mutex> lk(g_ring.mu);
+    int rc = ring_init();
+    if (rc) return rc;
+    const size_t row_bytes = (size_t)cols * 8;
+    if (row_bytes > D2H_SLOT_BYTES) {  // absurdly wide rows: let the driver stage it
+        KMG_CUDA_CHECK(cudaMemcpy2DAsync(dst, (size_t)ldk * 8, src, row_bytes, row_bytes, (size_t)rows, cudaMemcpyDeviceToHost, s));
+        KMG_CUDA_CHECK(cudaStreamSynchronize(s));
+        return KMG_OK;
+    }
+    const int64_t chunk_rows = std::max<int64_t>(1, (int64_t)(D2H_SLOT_BYTES / row_bytes));
+    std::future<int> fut[D2H_SLOTS];
+    int err = KMG_OK;
+    int slot = 0;
+    for (int64_t r = 0; r < rows; r += chunk_rows, slot = (slot + 1) % D2H_SLOTS) {
+        const int64_t nr = std::min<int64_t>(chunk_rows, rows - r);
+        if (fut[slot].valid() && fut[slot].get() != 0) err = KMG_ERR_CUDA;
+        if (err) break;
+        KMG_CUDA_CHECK(cudaMemcpyAsync(g_ring.buf[slot], src + r * cols, (size_t)nr * row_bytes, cudaMemcpyDeviceToHost, s));
+        KMG_CUDA_CHECK(cudaEventRecord(g_ring.ev[slot], s));
+        const char* stage = reinterpret_cast<const char*>(g_ring.buf[slot]);
+        cudaEvent_t ev = g_ring.ev[slot];
+        double* d0 = dst + r * ldk;
+        fut[slot] = std::async(std::launch::async, [=]() -> int {
+            if (cudaEventSynchronize(ev) != cudaSuccess) return 1;
+            if (ldk == cols) {
+                memcpy(d0, stage, (size_t)nr * row_bytes);
+            } else {
+                for (int64_t i = 0; i < nr; ++i) memcpy(d0 + i * ldk, stage + (size_t)i * row_bytes, row_bytes);
+            }
+            return 0;
+        });
+    }
+    for (int i = 0; i < D2H_SLOTS; ++i)
+        if (fut[i].valid() && fut[i].get() != 0) err = KMG_ERR_CUDA;
+    if (err) { kmg_set_error("device-to-host copy failed"); return err; }
     return KMG_OK;
 }
 
@@ -126,27 +253,28 @@ int build_to_host(int64_t nr, int64_t nc, bool symmetric, BlockFn fn, void* ctx,
     if (br >= nr) {
         DevBuf out;
         if ((rc = out.alloc((size_t)nr * nc * sizeof(double)))) return rc;
+        kmg_trace("build_to_host: output allocated");
         if ((rc = fn(ctx, 0, nr, out.as<double>(), nc, symmetric ? 1 : 0, s0))) return rc;
-        KMG_CUDA_CHECK(cudaMemcpy2DAsync(K, (size_t)ldk * 8, out.p, (size_t)nc * 8, (size_t)nc * 8, (size_t)nr, cudaMemcpyDeviceToHost, s0));
-        KMG_CUDA_CHECK(cudaStreamSynchronize(s0));
-        return KMG_OK;
+        if (getenv("KMG_TRACE")) { cudaStreamSynchronize(s0); kmg_trace("build_to_host: kernel done"); }
+        rc = d2h_rows(K, ldk, out.as<double>(), nc, nr, s0);
+        kmg_trace("build_to_host: copied to host");
+        return rc;
     }
-    // streamed: two buffers, compute of block b+1 overlaps the copy of block b
+    // streamed: two device buffers; the GPU builds block b+1 while block b drains to the host
     DevBuf buf[2];
     cudaStream_t st[2] = {s0, s1};
     for (int i = 0; i < 2; ++i)
         if ((rc = buf[i].alloc((size_t)br * nc * sizeof(double)))) return rc;
-    int which = 0;
-    for (int64_t r0 = 0; r0 < nr; r0 += br, which ^= 1) {
-        const int64_t rows = std::min<int64_t>(br, nr - r0);
-        cudaStream_t s = st[which];
-        KMG_CUDA_CHECK(cudaStreamSynchronize(s));  // previous copy out of this buffer finished
-        if ((rc = fn(ctx, r0, rows, buf[which].as<double>(), nc, 0, s))) return rc;
-        KMG_CUDA_CHECK(cudaMemcpy2DAsync(K + r0 * ldk, (size_t)ldk * 8, buf[which].p, (size_t)nc * 8, (size_t)nc * 8, (size_t)rows,
-                                         cudaMemcpyDeviceToHost, s));
+    const int64_t nblocks = (nr + br - 1) / br;
+    if ((rc = fn(ctx, 0, std::min<int64_t>(br, nr), buf[0].as<double>(), nc, 0, st[0]))) return rc;
+    for (int64_t b = 0; b < nblocks; ++b) {
+        const int64_t r0 = b * br, rows = std::min<int64_t>(br, nr - r0);
+        if (b + 1 < nblocks) {
+            const int64_t r1 = (b + 1) * br;
+            if ((rc = fn(ctx, r1, std::min<int64_t>(br, nr - r1), buf[(b + 1) & 1].as<double>(), nc, 0, st[(b + 1) & 1]))) return rc;
+        }
+        if ((rc = d2h_rows(K + r0 * ldk, ldk, buf[b & 1].as<double>(), nc, rows, st[b & 1]))) return rc;
     }
-    KMG_CUDA_CHECK(cudaStreamSynchronize(s0));
-    KMG_CUDA_CHECK(cudaStreamSynchronize(s1));
     return KMG_OK;
 }
 
@@ -233,7 +361,14 @@ int kmg_set_device(int device) {
     return KMG_OK;
 }
 
-int kmg_release(void) { return KMG_OK; }
+int kmg_release(void) {
+    std::lock_guard<std::mutex> lk(g_cache.mu);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    g_cache.flush();
+    cudaSetDevice(dev);
+    return KMG_OK;
+}
 
 int kmg_mismatch_table_host(int k, int m, int64_t* T) {
     KMG_REQUIRE(k >= 1 && k <= KMG_MAX_L && m >= 0 && T != nullptr, KMG_ERR_ARG, "mismatch_table: bad arguments");
@@ -264,7 +399,9 @@ int kmg_spectrum_host(const uint8_t* rows, int64_t nr, const uint8_t* cols, int6
         return kmg_mismatch_host(rows, nr, cols, nc, L, seq_format, ks[0], 0, 0, KMG_MM_PAIRWISE, K, ldk);
     }
     SeqPair sp;
+    kmg_trace("spectrum_host: enter");
     if ((rc = upload_pair(rows, nr, cols, nc, L, seq_format, &sp))) return rc;
+    kmg_trace("spectrum_host: sequences uploaded and packed");
     KMG_REQUIRE(K != nullptr && ldk >= sp.nc, KMG_ERR_ARG, "spectrum: bad output buffer");
     if (sp.nr == 0 || sp.nc == 0) return KMG_OK;
     cudaStream_t s;
@@ -280,6 +417,7 @@ int kmg_spectrum_host(const uint8_t* rows, int64_t nr, const uint8_t* cols, int6
         pc = phi_c.as<int8_t>();
     }
     KMG_CUDA_CHECK(cudaStreamSynchronize(s));
+    kmg_trace("spectrum_host: Phi built");
     SpectrumCtx ctx{phi_r.as<int8_t>(), pc, sp.nc, width, nullptr, nullptr};
     return build_to_host(sp.nr, sp.nc, sp.symmetric, spectrum_block, &ctx, K, ldk);
 }
@@ -633,6 +771,21 @@ int64_t kmg_center_workspace_bytes(int64_t n) { return kmg_ew_center_workspace(n
 
 int kmg_center_dev(const double* d_K, int64_t n, int64_t ld, double* d_out, int64_t ldo, void* d_workspace, void* stream) {
     return kmg_ew_center(d_K, n, ld, d_out, ldo, d_workspace, (cudaStream_t)stream);
+}
+
+int kmg_row_sums_dev(const double* d_K, int64_t rows, int64_t cols, int64_t ld, double* d_rs, void* stream) {
+    return kmg_ew_row_sums(d_K, rows, cols, ld, d_rs, (cudaStream_t)stream);
+}
+
+int64_t kmg_col_sums_workspace_bytes(int64_t rows, int64_t cols) { return kmg_ew_col_sums_workspace(rows, cols); }
+
+int kmg_col_sums_dev(const double* d_K, int64_t rows, int64_t cols, int64_t ld, double* d_cs, void* d_workspace, void* stream) {
+    return kmg_ew_col_sums(d_K, rows, cols, ld, d_cs, d_workspace, (cudaStream_t)stream);
+}
+
+int kmg_center_apply_dev(const double* d_K, int64_t rows, int64_t cols, int64_t n_total, int64_t ld, const double* d_rs,
+                         const double* d_cs, const double* d_g, double* d_out, int64_t ldo, void* stream) {
+    return kmg_ew_center_apply(d_K, rows, cols, n_total, ld, d_rs, d_cs, d_g, d_out, ldo, (cudaStream_t)stream);
 }
 
 int kmg_gather_dev(const double* d_K, int64_t ld, const int64_t* d_idx, int64_t m, double* d_out, int64_t ldo, void* stream) {

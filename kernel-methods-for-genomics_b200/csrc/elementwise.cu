@@ -110,12 +110,12 @@ __global__ void __launch_bounds__(256) vec_sum_kernel(const double* __restrict__
 }
 
 // out[i,j] = K[i,j] - cs[j]/n - rs[i]/n + g/n^2   (closed form of (I-11'/n) K (I-11'/n))
-__global__ void __launch_bounds__(256) center_apply_kernel(const double* __restrict__ K, int64_t n, int64_t ld,
+__global__ void __launch_bounds__(256) center_apply_kernel(const double* __restrict__ K, int64_t cols, int64_t n, int64_t ld,
                                                            const double* __restrict__ rs, const double* __restrict__ cs,
                                                            const double* __restrict__ g, double* __restrict__ out, int64_t ldo) {
     const int64_t j = blockIdx.x * 256ll + threadIdx.x;
     const int64_t i = blockIdx.y;
-    if (j >= n) return;
+    if (j >= cols) return;
     const double inv = 1.0 / (double)n;
     out[i * ldo + j] = K[i * ld + j] - cs[j] * inv - rs[i] * inv + (*g) * inv * inv;
 }
@@ -204,7 +204,7 @@ int kmg_ew_center(const double* K, int64_t n, int64_t ld, double* out, int64_t l
     col_sum_partial_kernel<<<dim3((unsigned)((n + 255) / 256), (unsigned)chunks), 256, 0, s>>>(K, n, n, ld, part);
     col_sum_final_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(part, chunks, n, cs);
     vec_sum_kernel<<<1, 256, 0, s>>>(rs, n, g);
-    center_apply_kernel<<<dim3((unsigned)((n + 255) / 256), (unsigned)n), 256, 0, s>>>(K, n, ld, rs, cs, g, out, ldo);
+    center_apply_kernel<<<dim3((unsigned)((n + 255) / 256), (unsigned)n), 256, 0, s>>>(K, n, n, ld, rs, cs, g, out, ldo);
     KMG_CUDA_CHECK(cudaGetLastError());
     return KMG_OK;
 }
@@ -236,6 +236,39 @@ int kmg_ew_weighted_dot(const double* A, int64_t lda, const double* B, int64_t l
     if (n <= 0) return KMG_OK;
     weighted_dot_partial_kernel<<<(unsigned)n, 256, 0, s>>>(A, lda, B, ldb, w, n, partial);
     vec_sum_kernel<<<1, 256, 0, s>>>(partial, n, result);
+    KMG_CUDA_CHECK(cudaGetLastError());
+    return KMG_OK;
+}
+
+// ---- pieces of the centring for a sharded (block-row) Gram: kmg/dist.py all-reduces the column sums
+int kmg_ew_row_sums(const double* K, int64_t rows, int64_t cols, int64_t ld, double* rs, cudaStream_t s) {
+    if (rows <= 0) return KMG_OK;
+    row_sum_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(K, rows, cols, ld, rs);
+    KMG_CUDA_CHECK(cudaGetLastError());
+    return KMG_OK;
+}
+
+int64_t kmg_ew_col_sums_workspace(int64_t rows, int64_t cols) {
+    return ((rows + CS_CHUNK - 1) / CS_CHUNK) * cols * (int64_t)sizeof(double);
+}
+
+int kmg_ew_col_sums(const double* K, int64_t rows, int64_t cols, int64_t ld, double* cs, void* workspace, cudaStream_t s) {
+    if (cols <= 0) return KMG_OK;
+    const int64_t chunks = (rows + CS_CHUNK - 1) / CS_CHUNK;
+    KMG_REQUIRE(chunks <= 65535, KMG_ERR_ARG, "col_sums: too many rows for one launch");
+    if (rows <= 0) { KMG_CUDA_CHECK(cudaMemsetAsync(cs, 0, (size_t)cols * 8, s)); return KMG_OK; }
+    double* part = reinterpret_cast<double*>(workspace);
+    col_sum_partial_kernel<<<dim3((unsigned)((cols + 255) / 256), (unsigned)chunks), 256, 0, s>>>(K, rows, cols, ld, part);
+    col_sum_final_kernel<<<(unsigned)((cols + 255) / 256), 256, 0, s>>>(part, chunks, cols, cs);
+    KMG_CUDA_CHECK(cudaGetLastError());
+    return KMG_OK;
+}
+
+int kmg_ew_center_apply(const double* K, int64_t rows, int64_t cols, int64_t n_total, int64_t ld, const double* rs, const double* cs,
+                        const double* g, double* out, int64_t ldo, cudaStream_t s) {
+    if (rows <= 0 || cols <= 0) return KMG_OK;
+    KMG_REQUIRE(rows <= 65535, KMG_ERR_ARG, "center_apply: too many rows for one launch");
+    center_apply_kernel<<<dim3((unsigned)((cols + 255) / 256), (unsigned)rows), 256, 0, s>>>(K, cols, n_total, ld, rs, cs, g, out, ldo);
     KMG_CUDA_CHECK(cudaGetLastError());
     return KMG_OK;
 }

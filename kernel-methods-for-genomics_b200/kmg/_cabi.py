@@ -59,6 +59,10 @@ PROTOTYPES = {
     "kmg_normalize_dev": (_i32, [_vp, _i64, _i64, _vp, _vp]),
     "kmg_center_workspace_bytes": (_i64, [_i64]),
     "kmg_center_dev": (_i32, [_vp, _i64, _i64, _vp, _i64, _vp, _vp]),
+    "kmg_row_sums_dev": (_i32, [_vp, _i64, _i64, _i64, _vp, _vp]),
+    "kmg_col_sums_workspace_bytes": (_i64, [_i64, _i64]),
+    "kmg_col_sums_dev": (_i32, [_vp, _i64, _i64, _i64, _vp, _vp, _vp]),
+    "kmg_center_apply_dev": (_i32, [_vp, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _i64, _vp]),
     "kmg_gather_dev": (_i32, [_vp, _i64, _vp, _i64, _vp, _i64, _vp]),
     "kmg_combine_dev": (_i32, [_vp, _vp, _vp, _i32, _i32, _i64, _i64, _vp, _i64, _vp]),
     "kmg_weighted_dot_dev": (_i32, [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _vp]),

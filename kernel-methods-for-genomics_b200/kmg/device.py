@@ -148,6 +148,28 @@ def center(K):
     return out
 
 
+def row_sums(K):
+    rows, cols = K.shape
+    rs = torch.empty(rows, dtype=torch.float64, device=K.device)
+    check(_cabi.lib().kmg_row_sums_dev(_p(K), rows, cols, K.stride(0), _p(rs), _stream()))
+    return rs
+
+
+def col_sums(K):
+    rows, cols = K.shape
+    cs = torch.empty(cols, dtype=torch.float64, device=K.device)
+    ws = torch.empty(max(int(_cabi.lib().kmg_col_sums_workspace_bytes(rows, cols)), 8), dtype=torch.uint8, device=K.device)
+    check(_cabi.lib().kmg_col_sums_dev(_p(K), rows, cols, K.stride(0), _p(cs), _p(ws), _stream()))
+    return cs
+
+
+def center_apply(K, rs, cs, g, n_total):
+    rows, cols = K.shape
+    out = torch.empty_like(K)
+    check(_cabi.lib().kmg_center_apply_dev(_p(K), rows, cols, n_total, K.stride(0), _p(rs), _p(cs), _p(g), _p(out), out.stride(0), _stream()))
+    return out
+
+
 def combine(Ks, u, degree=1):
     p = len(Ks)
     rows, cols = Ks[0].shape

@@ -1,0 +1,111 @@
+"""
+dist.py -- multi-GPU layer: one process per GPU, block-row sharding of the n x n Gram.
+
+Every Gram entry depends on two sequences only, so each rank holds ALL packed sequences (6.4 MB at n = 200 000),
+builds whatever feature matrix it needs locally and computes its own block-row: the construction needs no
+collective at all.  torch.distributed (NCCL over NVLink / NVSwitch on the GPU box, gloo in the CPU tests) is used
+only where the path has a real exchange:
+
+  * gather_rows      all-gather of block-rows when a consumer (the reference's solvers) needs the whole matrix on
+                     one device -- capacity limited (fp64: n <~ 140 000 per 180 GB GPU);
+  * center_sharded   centring of a sharded Gram: row sums are local (a block-row has every column); the column sums
+                     and the grand sum are one all-reduce of n + 1 doubles;
+  * frobenius_sharded  ALIGNF's <K_i, K_j>_F style reductions: one all-reduce of a scalar per pair.
+
+The partition / collective logic is backend agnostic (it is what the gloo tests cover); the arithmetic is supplied
+by the caller: `kmg.device` functions on the GPU, oracle functions in the CPU tests.
+"""
+import torch
+import torch.distributed as dist
+
+TILE_ALIGN = 256  # block-row boundaries are multiples of the GEMM tile height
+
+
+def block_rows(n, world, rank, align=TILE_ALIGN):
+    """Contiguous block-row [r0, r1) of rank `rank`: ceil(n / world) rounded up to `align`, last ranks may be short or empty."""
+    per = -(-n // world)
+    per = -(-per // align) * align
+    r0 = min(n, rank * per)
+    r1 = min(n, r0 + per)
+    return r0, r1
+
+
+def all_block_rows(n, world, align=TILE_ALIGN):
+    return [block_rows(n, world, r, align) for r in range(world)]
+
+
+def build_block_row(build_fn, n, group=None, align=TILE_ALIGN):
+    """Run `build_fn(r0, r1) -> tensor (r1-r0, n)` for this rank's block-row.  No communication."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    r0, r1 = block_rows(n, world, rank, align)
+    return r0, r1, build_fn(r0, r1)
+
+
+def gather_rows(block, n, group=None, align=TILE_ALIGN):
+    """All-gather the block-rows into the full (n, n) matrix on every rank (block: (r1-r0, n))."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return block
+    world = dist.get_world_size(group)
+    spans = all_block_rows(n, world, align)
+    per = max(r1 - r0 for r0, r1 in spans)
+    pad = torch.zeros((per, block.shape[1]), dtype=block.dtype, device=block.device)
+    pad[: block.shape[0]] = block
+    out = torch.empty((world * per, block.shape[1]), dtype=block.dtype, device=block.device)
+    dist.all_gather_into_tensor(out, pad, group=group)
+    if all(r1 - r0 == per for r0, r1 in spans):
+        return out[:n]
+    return torch.cat([out[r * per: r * per + (r1 - r0)] for r, (r0, r1) in enumerate(spans)], dim=0)
+
+
+def center_sharded(block, n, row_sum_fn, col_sum_fn, apply_fn, group=None):
+    """center_K (kernels.py:387-395) on a sharded Gram.  block: this rank's (rows, n) block-row.
+    row_sum_fn(block) -> (rows,), col_sum_fn(block) -> (n,) partial column sums of the block,
+    apply_fn(block, rs, cs, g, n) -> centred block  (K - cs/n - rs/n + g/n^2)."""
+    rs = row_sum_fn(block)
+    cs = col_sum_fn(block)
+    packed = torch.cat([cs, rs.sum().reshape(1)])
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=group)
+    return apply_fn(block, rs, packed[:-1].contiguous(), packed[-1:].contiguous(), n)
+
+
+def frobenius_sharded(block_a, block_b, dot_fn, group=None):
+    """<A, B>_F of two identically sharded matrices: local partial + one scalar all-reduce."""
+    part = dot_fn(block_a, block_b).reshape(1)
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(part, op=dist.ReduceOp.SUM, group=group)
+    return part
+
+
+# ---------------------------------------------------------------------------------------------------
+# GPU conveniences (thin: they only bind kmg.device to the functions above)
+# ---------------------------------------------------------------------------------------------------
+def spectrum_block_row(planes, L, ks, n, group=None, out_dtype=1):
+    """This rank's block-row of the (summed) spectrum Gram, device resident.  Phi is built locally."""
+    from . import device as kd
+    phi = kd.spectrum_phi(planes, L, ks)
+
+    def build(r0, r1):
+        return kd.gram_i8(phi[r0:r1], phi, row_index0=r0, col_index0=0, out_dtype=out_dtype)
+    return build_block_row(build, n, group)
+
+
+def wd_block_row(planes, L, d, n, group=None):
+    from . import device as kd
+    return build_block_row(lambda r0, r1: kd.wd_block(planes[r0:r1], planes, L, d, row_index0=r0), n, group)
+
+
+def mismatch_block_row(planes, L, k, m, n, normalize=True, group=None):
+    from . import device as kd
+    sd = kd.mismatch_diag_sqrt(planes, L, k, m) if normalize else None  # every rank computes all n diagonals: no collective
+
+    def build(r0, r1):
+        return kd.mismatch_block(planes[r0:r1], planes, L, k, m, row_index0=r0,
+                                 sd_rows=None if sd is None else sd[r0:r1], sd_cols=sd)
+    return build_block_row(build, n, group)
+
+
+def center_block_row(block, n, group=None):
+    from . import device as kd
+    return center_sharded(block, n, kd.row_sums, kd.col_sums, kd.center_apply, group)

@@ -1,0 +1,85 @@
+"""CPU: the C-ABI library loads and exports every symbol include/kmg.h declares; the host-side shim has the
+reference's surface; without a GPU every compute entry point fails loudly (no CPU fallback)."""
+import ctypes as C
+import inspect
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "kmg.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(kmg_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from kmg import _cabi
+    lib = _cabi.lib()
+    names = _declared_symbols()
+    assert len(names) >= 38
+    for name in names:
+        assert hasattr(lib, name), f"{name} declared in include/kmg.h but not exported by libkmg.so"
+        assert name in _cabi.PROTOTYPES, f"{name} has no ctypes prototype in kmg/_cabi.py"
+    assert set(_cabi.PROTOTYPES) == set(names)
+    assert lib.kmg_version() >= 100
+    # only libkmg's own symbols are bound: nothing from oracle/ is reachable from the product package
+    import kmg
+    src = "".join(open(os.path.join(os.path.dirname(kmg.__file__), f)).read() for f in os.listdir(os.path.dirname(kmg.__file__)) if f.endswith(".py"))
+    assert "oracle" not in src.replace("oracle functions in the CPU tests", "")
+
+
+def test_reference_surface():
+    """Same names and signatures as the reference's kernels.py."""
+    import kernels as km
+    sig = {n: list(inspect.signature(getattr(km, n)).parameters) for n in (
+        "select_method", "get_spectrum_K", "get_WD_K", "get_mismatch_K", "get_LA_K", "center_K", "normalize_K", "beta", "format",
+        "letter_to_num", "get_phi_u", "get_phi_km", "get_WD_d", "affine_align", "Smith_Waterman")}
+    assert sig["select_method"] == ["X", "method"]
+    assert sig["get_spectrum_K"] == ["X", "k"] and sig["get_WD_K"] == ["X", "d"] and sig["get_mismatch_K"] == ["X", "k", "m"]
+    assert sig["get_LA_K"] == ["X", "e", "d", "beta", "smith", "eig"]
+    assert inspect.signature(km.get_LA_K).parameters["beta"].default == 0.5
+    assert sig["get_WD_d"] == ["x", "y", "d", "L"] and sig["affine_align"] == ["x", "y", "e", "d", "beta"]
+    assert km.S.tolist() == [[4, 0, 0, 0], [0, 9, -3, -1], [0, -3, 6, 2], [0, -1, -2, 5]]
+    assert km.beta(10, 3) == 2 * (10 - 3 + 1) / 10 / 11
+    assert km.letter_to_num("ACGT") == "1234" and km.format("TTA").tolist() == [4, 4, 1]
+
+
+def test_mismatch_table_host_utility():
+    import oracle_np as onp
+    from kmg import host
+    for k, m in ((10, 1), (10, 2), (4, 2), (5, 0), (16, 3), (101, 1)):
+        assert host.mismatch_table(k, m).tolist() == onp.mismatch_table(k, m), (k, m)
+
+
+def test_no_cpu_fallback():
+    """On a box without a GPU the product path must fail, not compute."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from kmg import KmgError, host
+    codes = np.zeros((4, 101), np.uint8)
+    for call in (lambda: host.spectrum_gram(codes, 3), lambda: host.wd_gram(codes, 4), lambda: host.mismatch_gram(codes, 10, 1),
+                 lambda: host.la_gram(codes, -11, -1, 0.5), lambda: host.center(np.eye(3)), lambda: host.combine([np.eye(3)], [1.0])):
+        with pytest.raises(KmgError) as e:
+            call()
+        assert e.value.code == -1 and "no CPU fallback" in str(e.value)
+    K = np.eye(3) * 2
+    with pytest.raises(KmgError):
+        host.normalize_inplace(K)
+
+
+def test_argument_errors_are_value_errors():
+    from kmg import host
+    with pytest.raises(ValueError):
+        host.as_seq_buffer(["ACGT", "ACG"])
+    with pytest.raises(ValueError):
+        host.normalize_inplace(np.zeros((3, 4)))
+    buf, fmt = host.as_seq_buffer(["ACGT", "TTTT"])
+    assert buf.shape == (2, 4) and fmt == 1
+    buf, fmt = host.as_seq_buffer(np.zeros((2, 5), np.uint8))
+    assert fmt == 0

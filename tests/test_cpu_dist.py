@@ -1,0 +1,88 @@
+"""CPU: the multi-GPU host logic (kmg/dist.py) with gloo, world size 2 and 3: block-row partition, all-gather
+of ragged block-rows, sharded centring and sharded Frobenius products.  The per-block arithmetic is supplied by the
+oracle here (on the GPU box it is kmg.device); what is under test is the partition / collective plumbing."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, n, q):
+    for p in (os.path.join(ROOT, "kernel-methods-for-genomics_b200"), os.path.join(ROOT, "oracle")):
+        sys.path.insert(0, p)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import oracle_np as onp
+        from kmg import dist as kdist
+        codes = onp.synthetic_codes(n, 31, seed=9)
+        full = onp.spectrum_gram(codes, [1, 2, 3])
+        wd = onp.wd_gram(codes, 4)
+        # --- block rows: no communication, ragged last block (align 16 so that n=100 splits unevenly)
+        r0, r1, blk = kdist.build_block_row(lambda a, b: torch.from_numpy(full[a:b].copy()), n, align=16)
+        spans = kdist.all_block_rows(n, world, 16)
+        assert spans[rank] == (r0, r1) and spans[0][0] == 0 and spans[-1][1] == n
+        assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+        # --- all-gather of ragged block rows reproduces the full Gram bit for bit on every rank
+        got = kdist.gather_rows(blk, n, align=16)
+        assert got.shape == (n, n) and np.array_equal(got.numpy(), full)
+        # --- sharded centring == center_K of the full matrix (normwise 1e-12)
+        wblk = torch.from_numpy(wd[r0:r1].copy())
+        cen = kdist.center_sharded(
+            wblk, n,
+            row_sum_fn=lambda b: b.sum(1), col_sum_fn=lambda b: b.sum(0),
+            apply_fn=lambda b, rs, cs, g, nn: b - cs[None, :] / nn - rs[:, None] / nn + g / (nn * nn))
+        want = onp.center_K(wd)[r0:r1]
+        assert np.abs(cen.numpy() - want).max() <= 1e-12 * np.abs(wd).max()
+        # --- sharded Frobenius product (exact: integer-valued Grams)
+        fro = kdist.frobenius_sharded(blk, blk, lambda a, b: (a * b).sum())
+        assert float(fro) == float((full * full).sum())
+        q.put((rank, "ok"))
+    except Exception as e:  # pragma: no cover - reported to the parent
+        import traceback
+        q.put((rank, traceback.format_exc()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n", [(2, 100), (3, 100), (2, 32)])
+def test_gloo_block_row_sharding(world, n):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    for rank, msg in res:
+        assert msg == "ok", f"rank {rank}: {msg}"
+
+
+def test_block_rows_partition_properties():
+    sys.path.insert(0, os.path.join(ROOT, "kernel-methods-for-genomics_b200"))
+    from kmg import dist as kdist
+    for n in (0, 1, 255, 256, 257, 9000, 200_000):
+        for world in (1, 2, 4, 8):
+            spans = kdist.all_block_rows(n, world)
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            assert all(r0 % 256 == 0 or r0 == n for r0, _ in spans)
+    assert kdist.all_block_rows(200_000, 8) == [(i * 25088, min(200_000, (i + 1) * 25088)) for i in range(8)]
