@@ -71,6 +71,10 @@ int kmg_mismatch_phi_host(const uint8_t* seqs, int64_t n, int L, int seq_format,
 /* get_WD_K (kernels.py:84-101).  Symmetric: diagonal is the closed form of kernels.py:96. */
 int kmg_wd_host(const uint8_t* rows, int64_t nr, const uint8_t* cols, int64_t nc, int L, int seq_format,
                 int d, double* K, int64_t ldk);
+/* get_WDShifts_K (kernels.py:138-155): weighted degree with shifts 0..S, delta_s = 1/2/(s+1); fp64 accumulation in
+ * the reference's (k, i, s) order (bit-exact).  0 <= S <= 7. */
+int kmg_wds_host(const uint8_t* rows, int64_t nr, const uint8_t* cols, int64_t nc, int L, int seq_format,
+                 int d, int S, double* K, int64_t ldk);
 /* get_LA_K pair loop (kernels.py:287-291) with the INTENDED affine_align / Smith_Waterman
  * (kernels.py:226-270; the reference as written returns 0.0 for every pair -- see DESIGN.md). */
 int kmg_la_host(const uint8_t* rows, int64_t nr, const uint8_t* cols, int64_t nc, int L, int seq_format,
@@ -120,6 +124,8 @@ int kmg_mismatch_dev(const uint32_t* d_planes_rows, const uint32_t* d_planes_col
 int kmg_mismatch_diag_dev(const uint32_t* d_planes, int64_t n, int L, int k, int m, double* d_sd, void* stream);
 int kmg_wd_dev(const uint32_t* d_planes_rows, const uint32_t* d_planes_cols, int64_t rows, int64_t cols, int64_t row_index0,
                int64_t col_index0, int L, int d, double* d_out, int64_t ldo, int symmetric, void* stream);
+int kmg_wds_dev(const uint32_t* d_planes_rows, const uint32_t* d_planes_cols, int64_t rows, int64_t cols, int64_t row_index0,
+                int64_t col_index0, int L, int d, int S, double* d_out, int64_t ldo, int symmetric, void* stream);
 int kmg_la_dev(const uint32_t* d_planes_rows, const uint32_t* d_planes_cols, int64_t rows, int64_t cols, int64_t row_index0,
                int64_t col_index0, int L, double e, double d, double beta, int smith, double* d_out, int64_t ldo,
                int symmetric, void* stream);

@@ -337,6 +337,7 @@ int pair_block(void* c, int64_t r0, int64_t rows, double* out, int64_t ldo, int 
     b.sd_rows = x->sd ? x->sd + r0 : nullptr; b.sd_cols = x->sd;
     if (x->kind == 0) return kmg_mismatch_launch(&b, x->k, x->m, s);
     if (x->kind == 1) return kmg_wd_launch(&b, x->d, s);
+    if (x->kind == 3) return kmg_wds_launch(&b, x->d, x->k /* S */, s);
     return kmg_la_launch(&b, x->e, x->dd, x->beta, x->smith, s);
 }
 
@@ -515,6 +516,17 @@ int kmg_wd_host(const uint8_t* rows, int64_t nr, const uint8_t* cols, int64_t nc
     if ((rc = upload_pair(rows, nr, cols, nc, L, seq_format, &sp))) return rc;
     KMG_REQUIRE(K != nullptr && ldk >= sp.nc, KMG_ERR_ARG, "wd: bad output buffer");
     PairCtx ctx{&sp, L, 1, 0, 0, d, 0, 0.0, 0.0, 0.0, nullptr, sp.symmetric};
+    return build_to_host(sp.nr, sp.nc, sp.symmetric, pair_block, &ctx, K, ldk);
+}
+
+int kmg_wds_host(const uint8_t* rows, int64_t nr, const uint8_t* cols, int64_t nc, int L, int seq_format,
+                 int d, int S, double* K, int64_t ldk) {
+    int rc = require_device();
+    if (rc) return rc;
+    SeqPair sp;
+    if ((rc = upload_pair(rows, nr, cols, nc, L, seq_format, &sp))) return rc;
+    KMG_REQUIRE(K != nullptr && ldk >= sp.nc, KMG_ERR_ARG, "wds: bad output buffer");
+    PairCtx ctx{&sp, L, 3, /*k := S*/ S, 0, d, 0, 0.0, 0.0, 0.0, nullptr, sp.symmetric};
     return build_to_host(sp.nr, sp.nc, sp.symmetric, pair_block, &ctx, K, ldk);
 }
 
@@ -751,6 +763,13 @@ int kmg_wd_dev(const uint32_t* d_planes_rows, const uint32_t* d_planes_cols, int
     PairBlock b = make_block(d_planes_rows, d_planes_cols, rows, cols, row_index0, col_index0, L, d_out, ldo, KMG_OUT_F64, symmetric,
                              nullptr, nullptr);
     return kmg_wd_launch(&b, d, (cudaStream_t)stream);
+}
+
+int kmg_wds_dev(const uint32_t* d_planes_rows, const uint32_t* d_planes_cols, int64_t rows, int64_t cols, int64_t row_index0,
+                int64_t col_index0, int L, int d, int S, double* d_out, int64_t ldo, int symmetric, void* stream) {
+    PairBlock b = make_block(d_planes_rows, d_planes_cols, rows, cols, row_index0, col_index0, L, d_out, ldo, KMG_OUT_F64, symmetric,
+                             nullptr, nullptr);
+    return kmg_wds_launch(&b, d, S, (cudaStream_t)stream);
 }
 
 int kmg_la_dev(const uint32_t* d_planes_rows, const uint32_t* d_planes_cols, int64_t rows, int64_t cols, int64_t row_index0,

@@ -329,6 +329,93 @@ wd_kernel(const uint32_t* __restrict__ prow, const uint32_t* __restrict__ pcol, 
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// weighted degree with shifts (kernels.py:106-155)
+//   c_t = sum_k beta_k * c_st(k),   c_st(k) = sum_{i=1}^{L-k} sum_{s=0}^{S} [s+i<L] delta_s *
+//            ([x[i+s:i+s+k]==y[i:i+k]] + [x[i:i+k]==y[i+s:i+s+k]]),   delta_s = 1/2/(s+1)
+// The reference accumulates c_st sequentially over (i, s) in fp64; delta_2 = 1/6 is inexact, so
+// the order matters for bit-exactness.  Zero terms add +0.0 (a no-op), so only the set bits of the
+// run vectors are visited, in ascending i then ascending s.
+// ------------------------------------------------------------------------------------------
+struct WdsParams {
+    int d, S, L;
+    double beta[128];
+    double delta[8];
+};
+
+template <int SMAX>
+__global__ void __launch_bounds__(TILE_R * TILE_C)
+wds_kernel(const uint32_t* __restrict__ prow, const uint32_t* __restrict__ pcol, const OutSpec o, const WdsParams wp) {
+    __shared__ double tile[TILE_R][TILE_C + 1];
+    const int64_t r0 = (int64_t)blockIdx.y * TILE_R, c0 = (int64_t)blockIdx.x * TILE_C;
+    const int cls = tile_class(o, r0, c0);
+    if (cls == 2) return;
+    const int tr = threadIdx.x >> 5, tc = threadIdx.x & 31;
+    const int64_t r = r0 + tr, c = c0 + tc;
+    const bool live = r < o.rows && c < o.cols;
+    const SeqPlanes x = kmg_load_planes(prow, live ? r : 0);
+    const SeqPlanes y = kmg_load_planes(pcol, live ? c : 0);
+    uint32_t ca[SMAX + 1][4], cb[SMAX + 1][4], sa[SMAX + 1][4], sb[SMAX + 1][4];
+    {
+        uint32_t xl[4] = {x.lo[0], x.lo[1], x.lo[2], x.lo[3]}, xh[4] = {x.hi[0], x.hi[1], x.hi[2], x.hi[3]};
+        uint32_t yl[4] = {y.lo[0], y.lo[1], y.lo[2], y.lo[3]}, yh[4] = {y.hi[0], y.hi[1], y.hi[2], y.hi[3]};
+#pragma unroll
+        for (int s = 0; s <= SMAX; ++s) {
+            uint32_t vm[4] = {0u, 0u, 0u, 0u};
+            if (s <= wp.S && wp.L - 1 - s >= 0) kmg_range_mask_128(0, wp.L - 1 - s, vm);
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+                ca[s][w] = ~((xl[w] ^ y.lo[w]) | (xh[w] ^ y.hi[w])) & vm[w];  // bit i: x[i+s] == y[i]
+                cb[s][w] = ~((x.lo[w] ^ yl[w]) | (x.hi[w] ^ yh[w])) & vm[w];  // bit i: x[i] == y[i+s]
+                sa[s][w] = ca[s][w];
+                sb[s][w] = cb[s][w];
+            }
+            kmg_shr1_128(xl); kmg_shr1_128(xh); kmg_shr1_128(yl); kmg_shr1_128(yh);
+        }
+    }
+    double c_t = 0.0;
+#pragma unroll 1
+    for (int k = 1; k <= wp.d; ++k) {
+        if (k > 1) {
+#pragma unroll
+            for (int s = 0; s <= SMAX; ++s) {
+                kmg_shr1_128(sa[s]);
+                kmg_shr1_128(sb[s]);
+#pragma unroll
+                for (int w = 0; w < 4; ++w) { ca[s][w] &= sa[s][w]; cb[s][w] &= sb[s][w]; }
+            }
+        }
+        uint32_t st[4] = {0u, 0u, 0u, 0u};
+        if (wp.L - k >= 1) kmg_range_mask_128(1, wp.L - k, st);  // window starts i = 1 .. L-k
+        double c_st = 0.0;
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            uint32_t u = 0u;
+#pragma unroll
+            for (int s = 0; s <= SMAX; ++s) u |= ca[s][w] | cb[s][w];
+            u &= st[w];
+            while (u) {
+                const int bit = __ffs(u) - 1;
+                u &= u - 1;
+#pragma unroll
+                for (int s = 0; s <= SMAX; ++s) {
+                    const int m = (int)((ca[s][w] >> bit) & 1u) + (int)((cb[s][w] >> bit) & 1u);
+                    if (m) c_st = __dadd_rn(c_st, __dmul_rn(wp.delta[s], (double)m));
+                }
+            }
+        }
+        c_t = __dadd_rn(c_t, __dmul_rn(wp.beta[k - 1], c_st));
+    }
+    if (live) reinterpret_cast<double*>(o.out)[r * o.ldo + c] = c_t;
+    if (cls == 1) {
+        tile[tr][tc] = c_t;
+        __syncthreads();
+        const int mc = threadIdx.x >> 3, mr = threadIdx.x & 7;
+        if (r0 + mr < o.rows && c0 + mc < o.cols)
+            reinterpret_cast<double*>(o.out_t)[(c0 + mc) * o.ldo_t + r0 + mr] = tile[mr][mc];
+    }
+}
+
 int check_block(const PairBlock* b) {
     KMG_REQUIRE(b->rows >= 0 && b->cols >= 0, KMG_ERR_ARG, "negative block shape");
     KMG_REQUIRE(b->L >= 1 && b->L <= KMG_MAX_L, KMG_ERR_UNSUPPORTED, "sequence length %d not supported (1..%d)", b->L, KMG_MAX_L);
@@ -461,6 +548,27 @@ int kmg_wd_launch(const PairBlock* b, int d, cudaStream_t stream) {
     const OutSpec o = make_out(b);
     dim3 grid((unsigned)((b->cols + TILE_C - 1) / TILE_C), (unsigned)((b->rows + TILE_R - 1) / TILE_R));
     wd_kernel<<<grid, TILE_R * TILE_C, 0, stream>>>(b->planes_rows, b->planes_cols, o, wp);
+    KMG_CUDA_CHECK(cudaGetLastError());
+    return KMG_OK;
+}
+
+int kmg_wds_launch(const PairBlock* b, int d, int S, cudaStream_t stream) {
+    int rc = check_block(b);
+    if (rc) return rc;
+    KMG_REQUIRE(d >= 1 && d <= 127, KMG_ERR_ARG, "weighted degree with shifts: need 1 <= d <= 127 (d=%d)", d);
+    KMG_REQUIRE(S >= 0 && S <= 7, KMG_ERR_UNSUPPORTED, "weighted degree with shifts: 0 <= S <= 7 supported (S=%d)", S);
+    KMG_REQUIRE(b->out_dtype == KMG_OUT_F64 && b->sd_rows == nullptr, KMG_ERR_ARG, "weighted degree with shifts Gram is raw fp64");
+    if (b->rows == 0 || b->cols == 0) return KMG_OK;
+    WdsParams wp;
+    wp.d = d; wp.S = S; wp.L = b->L;
+    for (int k = 1; k <= 128; ++k)
+        wp.beta[k - 1] = k <= d ? (double)(2 * (d - k + 1)) / (double)d / (double)(d + 1) : 0.0;  // kernels.py:61
+    for (int s = 0; s < 8; ++s) wp.delta[s] = 1.0 / 2.0 / (double)(s + 1);                        // kernels.py:112
+    const OutSpec o = make_out(b);
+    dim3 grid((unsigned)((b->cols + TILE_C - 1) / TILE_C), (unsigned)((b->rows + TILE_R - 1) / TILE_R));
+    if (S <= 1) wds_kernel<1><<<grid, TILE_R * TILE_C, 0, stream>>>(b->planes_rows, b->planes_cols, o, wp);
+    else if (S <= 3) wds_kernel<3><<<grid, TILE_R * TILE_C, 0, stream>>>(b->planes_rows, b->planes_cols, o, wp);
+    else wds_kernel<7><<<grid, TILE_R * TILE_C, 0, stream>>>(b->planes_rows, b->planes_cols, o, wp);
     KMG_CUDA_CHECK(cudaGetLastError());
     return KMG_OK;
 }

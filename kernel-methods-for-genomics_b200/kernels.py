@@ -162,8 +162,21 @@ def normalize_K(K):
 # ------------------------------------------------------------------------------------------------
 # Select method (kernels.py:461-505)
 # ------------------------------------------------------------------------------------------------
+def delta(s):
+    """kernels.py:106-112."""
+    return 1/2/(s+1)
+
+
+def get_WDShifts_d(x, y, d, S, L):
+    """kernels.py:115-135 -- one pair."""
+    if len(x) != L or len(y) != L:
+        raise ValueError("get_WDShifts_d: sequences must have length L")
+    return float(_host.wds_gram([x], int(d), int(S), cols=[y])[0, 0])
+
+
 def get_WDShifts_K(X, d, S):
-    raise NotImplementedError("WDS (weighted degree with shifts, kernels.py:106-155) is a 'next' row of SURVEY.md section 8(f)")
+    """kernels.py:138-155 -- weighted degree with shifts (first 'next' row of SURVEY.md section 8f)."""
+    return _host.wds_gram(_seqs(X), int(d), int(S))
 
 
 def get_string_K(X, lbda, k):

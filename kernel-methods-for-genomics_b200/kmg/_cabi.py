@@ -39,6 +39,8 @@ PROTOTYPES = {
     "kmg_spectrum_phi_host": (_i32, [_vp, _i64, _i32, _i32, _vp, _i32, _vp, _i64]),
     "kmg_mismatch_phi_host": (_i32, [_vp, _i64, _i32, _i32, _i32, _i32, _vp, _i64]),
     "kmg_wd_host": (_i32, [_vp, _i64, _vp, _i64, _i32, _i32, _i32, _vp, _i64]),
+    "kmg_wds_host": (_i32, [_vp, _i64, _vp, _i64, _i32, _i32, _i32, _i32, _vp, _i64]),
+    "kmg_wds_dev": (_i32, [_vp, _vp, _i64, _i64, _i64, _i64, _i32, _i32, _i32, _vp, _i64, _i32, _vp]),
     "kmg_la_host": (_i32, [_vp, _i64, _vp, _i64, _i32, _i32, _dbl, _dbl, _dbl, _i32, _vp, _i64]),
     "kmg_normalize_host": (_i32, [_vp, _i64, _i64]),
     "kmg_center_host": (_i32, [_vp, _i64, _i64, _vp, _i64]),

@@ -125,6 +125,14 @@ def wd_block(planes_rows, planes_cols, L, d, row_index0=0, col_index0=0, symmetr
     return out
 
 
+def wds_block(planes_rows, planes_cols, L, d, S, row_index0=0, col_index0=0, symmetric=False, out=None):
+    rows, cols = planes_rows.shape[0], planes_cols.shape[0]
+    out = _out(rows, cols, KMG_OUT_F64, planes_rows.device, out)
+    check(_cabi.lib().kmg_wds_dev(_p(planes_rows), _p(planes_cols), rows, cols, row_index0, col_index0, L, d, S,
+                                  _p(out), out.stride(0), 1 if symmetric else 0, _stream()))
+    return out
+
+
 def la_block(planes_rows, planes_cols, L, e, d, beta, smith=0, row_index0=0, col_index0=0, symmetric=False, out=None):
     rows, cols = planes_rows.shape[0], planes_cols.shape[0]
     out = _out(rows, cols, KMG_OUT_F64, planes_rows.device, out)

@@ -106,6 +106,15 @@ def wd_gram(rows, d, cols=None):
     return K
 
 
+def wds_gram(rows, d, S, cols=None):
+    """Weighted-degree-with-shifts Gram (get_WDShifts_K, kernels.py:138-155)."""
+    rbuf, cbuf, fmt, nr, nc = _pair(rows, cols)
+    K = np.zeros((nr, nc), np.float64)
+    L = rbuf.shape[1] if nr else 1
+    check(_cabi.lib().kmg_wds_host(_ptr(rbuf), nr, _ptr(cbuf), 0 if cbuf is None else nc, L, fmt, int(d), int(S), _ptr(K), max(nc, 1)))
+    return K
+
+
 def la_gram(rows, e, d, beta, smith=0, cols=None):
     """Local-alignment Gram with the INTENDED recursion (kernels.py:226-291 as meant)."""
     rbuf, cbuf, fmt, nr, nc = _pair(rows, cols)

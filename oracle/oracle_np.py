@@ -181,6 +181,34 @@ def wd_gram(codes, d):
     return K
 
 
+def wds_pair(x, y, d, S, L):
+    """get_WDShifts_d (kernels.py:115-135) on byte strings: slices that run past the end are shorter and
+    therefore unequal, exactly as with the reference's Python strings; fp64 accumulation in the same order."""
+    c_t = 0
+    for k in range(1, d + 1):
+        beta_k = wd_beta(d, k)
+        c_st = 0
+        for i in range(1, L - k + 1):
+            for s in range(0, S + 1):
+                if s + i < L:
+                    c_st += (1 / 2 / (s + 1)) * ((x[i + s:i + s + k] == y[i:i + k]) + (x[i:i + k] == y[i + s:i + s + k]))
+        c_t += beta_k * c_st
+    return c_t
+
+
+def wds_gram(codes, d, S):
+    """get_WDShifts_K (kernels.py:138-155): j >= i computed (diagonal included, no closed form), mirrored."""
+    codes = np.asarray(codes, np.uint8)
+    n, L = codes.shape
+    seqs = [bytes(r) for r in codes]
+    K = np.zeros((n, n))
+    for i in range(n):
+        for j in range(i, n):
+            K[i, j] = wds_pair(seqs[i], seqs[j], d, S, L)
+            K[j, i] = K[i, j]
+    return K
+
+
 # --------------------------------------------------------------------------------------
 # mismatch kernel  (kernels.py:161-217)
 # --------------------------------------------------------------------------------------

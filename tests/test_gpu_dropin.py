@@ -137,3 +137,39 @@ def test_alignf_nlck_algebra(golden):
         assert np.abs(Km - golden[f"nlck_Km_deg{deg}"]).max() <= 1e-12, deg
         if deg <= 2:
             assert np.array_equal(Km, golden[f"nlck_Km_deg{deg}"]), deg     # deg 1, 2: bit-exact (x*x == np.square)
+
+
+def test_wds_dropin(km, golden, X0):
+    assert np.array_equal(km.select_method(X0.iloc[:12], "WDS_d3_s2"), golden["wds_d3_s2_n12"])
+    assert np.array_equal(km.get_WDShifts_K(X0.iloc[:10], 5, 1), golden["wds_d5_s1_n10"])
+    assert km.get_WDShifts_d(X0.seq[0], X0.seq[1], 3, 2, 101) == golden["wds_d3_s2_n12"][0, 1]
+    assert km.delta(2) == 1 / 2 / 3
+
+
+def test_alignf_nlck_classes(golden, X0, dna, capsys):
+    """The drop-in ALIGNF / NLCK classes (same constructor and methods as the reference's) against the values the
+    reference's own classes produced on the same kernels (oracle/gen_golden.py)."""
+    import ALIGNF as A
+    import NLCKernels as N
+    _, labels = dna
+    n_all = 96
+    Xa = X0.iloc[:n_all].copy()
+    ya = pd.DataFrame({"Id": np.arange(n_all), "Bound": labels[:n_all].astype(float)})
+    rows = golden["alignf_fit_rows"]
+    Ks = [golden[f"alignf_K{i}"].copy() for i in range(3)]
+    np.random.seed(11)
+    al = A.ALIGNF(Xa.iloc[rows], ya.iloc[rows], np.arange(n_all), Ks)
+    scale = np.sqrt(np.outer(np.diag(golden["alignf_M"]), np.diag(golden["alignf_M"])))
+    assert np.all(np.abs(al.M - golden["alignf_M"]) <= 1e-10 * scale)
+    assert np.allclose(al.a, golden["alignf_a"], rtol=1e-10, atol=1e-12 * np.abs(golden["alignf_a"]).max())
+    assert np.allclose(al.u_star, golden["alignf_u"], atol=1e-8)
+    Km = al.get_K()
+    assert np.abs(Km - golden["alignf_Km"]).max() <= 1e-8 * np.abs(golden["alignf_Km"]).max()
+    u, alpha = golden["nlck_u"], golden["nlck_alpha"]
+    for deg in (1, 2, 3):
+        nl = N.NLCK(Xa.iloc[rows], ya.iloc[rows], np.arange(n_all), [golden[f"alignf_K{i}"].copy() for i in range(3)], degree=deg)
+        ref = golden[f"nlck_grad_deg{deg}"]
+        assert np.all(np.abs(nl.grad(u, alpha) - ref) <= 1e-12 * np.abs(ref).max())
+        nl.fit = lambda *a, **k: u   # skip the cvxopt QP exactly as gen_golden.py did
+        assert np.abs(nl.get_K() - golden[f"nlck_Km_deg{deg}"]).max() <= 1e-12
+    capsys.readouterr()

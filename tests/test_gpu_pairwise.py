@@ -166,3 +166,20 @@ def test_la_smith_and_shapes(kh, dna):
     want = oc.la_block(c[:3], c[5:9], -11, -1, 0.5, 0, 0, 1 << 40)
     got = kh.la_gram(c[:3], -11, -1, 0.5, 0, cols=c[5:9])
     assert np.all(np.abs(got - want) <= LA_RTOL * np.abs(want))
+
+
+# ------------------------------------------------------------------ weighted degree with shifts
+def test_wds_golden_and_oracle(kd, kh, golden, dna):
+    codes, _ = dna
+    assert np.array_equal(kh.wds_gram(codes[:12], 3, 2), golden["wds_d3_s2_n12"])
+    assert np.array_equal(kh.wds_gram(codes[:10], 5, 1), golden["wds_d5_s1_n10"])
+    c = codes[500:540]
+    for d, S in ((4, 0), (6, 3), (10, 2), (3, 7), (12, 5)):
+        want = onp.wds_gram(c, d, S)
+        assert np.array_equal(kh.wds_gram(c, d, S), want), (d, S)
+    planes = kd.pack(c, 0)
+    want = onp.wds_gram(c, 5, 2)
+    assert np.array_equal(kd.wds_block(planes[8:24], planes, 101, 5, 2, row_index0=8).cpu().numpy(), want[8:24])
+    assert np.array_equal(kd.wds_block(planes, planes, 101, 5, 2, symmetric=True).cpu().numpy(), want)
+    cc = onp.synthetic_codes(20, 37, seed=4)
+    assert np.array_equal(kh.wds_gram(cc, 6, 4), onp.wds_gram(cc, 6, 4))

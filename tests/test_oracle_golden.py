@@ -149,3 +149,10 @@ def test_sha256_known_answers(golden, dna):
     K = onp.spectrum_gram(c1, 6)
     assert _sha(K) == kat["sp_k6_Xtr0_Xte0_3000"]
     assert K.sum() == 33300484.0 and np.trace(K) == 314044.0
+
+
+def test_wds_bit_exact(golden, dna):
+    """weighted degree with shifts (first 'next' row); delta_2 = 1/6 makes the order matter."""
+    codes, _ = dna
+    assert np.array_equal(onp.wds_gram(codes[:12], 3, 2), golden["wds_d3_s2_n12"])
+    assert np.array_equal(onp.wds_gram(codes[:10], 5, 1), golden["wds_d5_s1_n10"])
