@@ -212,7 +212,7 @@ def main():
 
     def step():
         kd.spectrum_phi(planes, L, KS, out=phi)
-        kd.gram_i8(phi[row0:row0 + R], phi, row_index0=row0, col_index0=0, out_dtype=1, m_sub=2, out=out)
+        kd.gram_i8(phi[row0:row0 + R], phi, row_index0=row0, col_index0=0, out_dtype=1, m_sub=0, out=out)
 
     def barrier():
         if dist is not None:
@@ -231,7 +231,7 @@ def main():
     for i in range(args.steps):
         kd.spectrum_phi(planes, L, KS, out=phi)
         ev[2 * i + 1].record()
-        kd.gram_i8(phi[row0:row0 + R], phi, row_index0=row0, col_index0=0, out_dtype=1, m_sub=2, out=out)
+        kd.gram_i8(phi[row0:row0 + R], phi, row_index0=row0, col_index0=0, out_dtype=1, m_sub=0, out=out)
         ev[2 * i + 2].record()
     ev[-1].record()
     barrier()
@@ -246,13 +246,13 @@ def main():
     entries_per_step = float(R) * n * world
     value = entries_per_step / (ms_per_step * 1e-3)
 
-    # ---- roofline of the dominant kernel (gram_i8_tcgen05_kernel<2>): tensor bound
+    # ---- roofline of the dominant kernel (gram_i8_2cta_kernel, the CTA-pair tcgen05 GEMM): tensor bound
     gemm_avg_ms = float(np.mean(gemm_ms))
     alg_ops = 2.0 * D_ALG * R * n  # 2*D ops per delivered entry, one launch = one block-row
     achieved_tops = alg_ops / (gemm_avg_ms * 1e-3) / 1e12
     peak_tops = 2.0 * peaks["bf16_sustained"]
     roofline = {
-        "kernel": "gram_i8_tcgen05_kernel<M_SUB=2>", "bound": "tensor", "achieved": achieved_tops, "peak": peak_tops,
+        "kernel": "gram_i8_2cta_kernel (tcgen05.mma.cta_group::2.kind::i8, 256x256 pair tile)", "bound": "tensor", "achieved": achieved_tops, "peak": peak_tops,
         "unit": "TOP/s (int8)", "frac": achieved_tops / peak_tops,
         "peak_source": f"2 x bf16_tflops_sustained of MEASURED_PEAKS.json ({peaks['source']}): the file has no int8 entry and the "
                        "tcgen05 kind::i8 rate is twice kind::f16; a cuBLAS bf16 denominator doubled, so a tight int8 kernel can read above 1.0",
@@ -311,8 +311,9 @@ def main():
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel, from the ncu --set full
-# capture summarised under profiles/ (null until a capture of this exact launch exists)
-TRAFFIC_BYTES_PER_LAUNCH = None
+# capture summarised in profiles/r1_gemm_ncu_full_summary.txt (81.23 GB read + 39.96 GB written; the algorithmic
+# minimum is 40 GB written + 4.4 GB of Phi read once -- the reads are the B panels re-streamed once per 8-row-tile band)
+TRAFFIC_BYTES_PER_LAUNCH = 121_185_340_000
 
 
 def extras(kd, torch, codes, planes, phi, peaks):

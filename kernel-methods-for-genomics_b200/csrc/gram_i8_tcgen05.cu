@@ -54,6 +54,8 @@ struct KernelParams {
     const int4* tiles;  // {row_tile, col_tile, mirror, 0}
     uint32_t* wave_counter;  // grid-wide arrival counter (zeroed before the launch) or null
     uint64_t hint_a, hint_b;  // L2 eviction policy of the A / B operand loads
+    int32_t prefetch_dist;    // k-blocks of L2 prefetch ahead of the smem pipeline (0 = off)
+    uint32_t dbg_b_bytes;     // timing experiment only: bytes of B actually loaded per stage (0 = all)
 };
 
 template <int M_SUB>
@@ -65,34 +67,63 @@ struct Cfg {
     static constexpr uint32_t A_BYTES = BM * BK;
     static constexpr uint32_t B_BYTES = BN * BK;
     static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr uint32_t EPI_STAGE_WORDS = 32 * 33;  // per epilogue warp: 32 x 32 int32 transpose tile, padded
+    static constexpr uint32_t EPI_STAGE_WORDS = 32 * 32;  // per epilogue warp: 32 x 32 int32 transpose tile, XOR-swizzled
     static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/ + NUM_EPI_WARPS * EPI_STAGE_WORDS * 4;
 };
 
 // Epilogue store of one 32-row x 32-column accumulator chunk.  After tcgen05.ld thread t holds row t, so a
 // direct store would touch 32 different cache lines per instruction (measured: the LSU wavefronts of that pattern
-// cost ~17 us per 256x256 tile).  Instead the chunk is transposed through a per-warp shared-memory tile
-// (row stride 33 words: conflict-free both ways) and every warp store writes 32 consecutive entries of one row.
-// The mirrored store K[c][r] needs no transpose: for a fixed register j the 32 lanes are 32 consecutive rows.
-__device__ __forceinline__ void store_chunk(const KernelParams& p, const uint32_t (&v)[32], uint32_t* stage /*[32][33]*/,
+// cost ~17 us per 256x256 tile).  Instead the chunk is transposed through a per-warp 4 KB shared-memory tile
+// (32 rows x 128 B, 16-byte chunks XOR-swizzled by row so that both the 128-bit row writes and the 64-bit
+// transposed reads are conflict-free); a half-warp then stores 32 consecutive entries of one row, 16 B per lane.
+// int32 -> fp64 uses the 2^52 magic-number add (one DADD) instead of the quarter-rate I2F.F64; accumulators are
+// non-negative counts.  The mirrored store K[c][r] needs no transpose: for a fixed register j the 32 lanes are
+// 32 consecutive rows.
+// Exact int -> double with integer instructions only (FLO + shifts): while the tensor pipe is saturated by the next
+// tile's UTCIMMA stream every FP64-pipe instruction of the epilogue (I2F.F64, or the 2^52 magic-number DADD) sits in
+// `stall_math` (ncu: a third of the epilogue warps' samples), integer ALU ops do not.  0 <= v < 2^31.
+// Where the epilogue runs in series with the main loop (tensor pipe idle) the one-instruction 2^52 magic-number DADD is
+// the cheaper conversion; INT_CVT selects per kernel.
+template <bool INT_CVT>
+__device__ __forceinline__ double u32_to_f64(uint32_t v) {
+    if (!INT_CVT) return __hiloint2double(0x43300000, (int)v) - 4503599627370496.0;
+    const int lz = __clz((int)v);                    // 32 for v == 0
+    const uint32_t w = (v << (lz & 31)) << 1;        // fraction bits left-aligned, leading one shifted out
+    const uint32_t hi = v ? (((1023u + 31u - (uint32_t)lz) << 20) | (w >> 12)) : 0u;
+    return __hiloint2double((int)hi, (int)(w << 20));
+}
+
+template <bool INT_CVT>
+__device__ __forceinline__ void store_chunk(const KernelParams& p, const uint32_t (&v)[32], uint32_t* stage /*4 KB*/,
                                             int lane, int64_t row_base, int64_t col0, bool mirror) {
     const int64_t ncol = (p.cols - col0 < 32) ? (p.cols - col0) : 32;  // warp-uniform, > 0
-    const int64_t row_t = row_base + lane;                             // the row this thread holds in registers
-    const int64_t col = col0 + lane;                                   // the column this thread stores
-    const bool col_ok = lane < ncol;
     int64_t nrow = p.rows - row_base;
     if (nrow > 32) nrow = 32;
     if (nrow <= 0) return;  // warp-uniform
+    {
+        uint4* srow = reinterpret_cast<uint4*>(stage + lane * 32);
 #pragma unroll
-    for (int j = 0; j < 32; ++j) stage[lane * 33 + j] = v[j];
+        for (int c = 0; c < 8; ++c) srow[c ^ (lane & 7)] = make_uint4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+    }
     __syncwarp();
+    const int half = lane >> 4, l16 = lane & 15;
+    const int64_t col = col0 + 2 * l16;  // this lane stores columns col, col+1
+    const int ok = (2 * l16 + 1 < ncol) ? 2 : ((2 * l16 < ncol) ? 1 : 0);
+    const bool norm = p.sd_rows != nullptr;
     if (p.out_dtype == KMG_OUT_S32) {
-        int32_t* dst = reinterpret_cast<int32_t*>(p.out) + row_base * p.ldo + col;
-        if (col_ok) {
-#pragma unroll 8
-            for (int rr = 0; rr < 32; ++rr)
-                if (rr < nrow) dst[(int64_t)rr * p.ldo] = (int32_t)stage[rr * 33 + lane];
+        int32_t* base = reinterpret_cast<int32_t*>(p.out);
+        const bool vec = ((p.ldo & 1) == 0) && ((reinterpret_cast<uintptr_t>(base) & 7) == 0);
+#pragma unroll 4
+        for (int r2 = 0; r2 < 16; ++r2) {
+            const int rr = 2 * r2 + half;
+            const uint2 iv = *reinterpret_cast<const uint2*>(stage + rr * 32 + (((l16 >> 1) ^ (rr & 7)) << 2) + ((l16 & 1) << 1));
+            if (rr < nrow && ok) {
+                int32_t* dst = base + (row_base + rr) * p.ldo + col;
+                if (ok == 2 && vec) *reinterpret_cast<int2*>(dst) = make_int2((int)iv.x, (int)iv.y);
+                else { dst[0] = (int)iv.x; if (ok == 2) dst[1] = (int)iv.y; }
+            }
         }
+        const int64_t row_t = row_base + lane;
         if (mirror && row_t < p.rows) {
             int32_t* dt = reinterpret_cast<int32_t*>(p.out_t) + col0 * p.ldo_t + row_t;
 #pragma unroll
@@ -100,30 +131,41 @@ __device__ __forceinline__ void store_chunk(const KernelParams& p, const uint32_
                 if (j < ncol) dt[(int64_t)j * p.ldo_t] = (int32_t)v[j];
         }
     } else {
-        double* dst = reinterpret_cast<double*>(p.out) + row_base * p.ldo + col;
-        const bool norm = p.sd_rows != nullptr;
-        const double sc = (norm && col_ok) ? p.sd_cols[col] : 1.0;
-        if (col_ok) {
-#pragma unroll 8
-            for (int rr = 0; rr < 32; ++rr) {
-                if (rr < nrow) {
-                    double val = (double)(int32_t)stage[rr * 33 + lane];
-                    if (norm) {
-                        // normalize_K (kernels.py:408-414): K_ij / (sqrt(K_ii) * sqrt(K_jj)), diagonal := 1.0
-                        val = __ddiv_rn(val, __dmul_rn(p.sd_rows[row_base + rr], sc));
-                        if (p.row_index0 + row_base + rr == p.col_index0 + col) val = 1.0;
-                    }
-                    dst[(int64_t)rr * p.ldo] = val;
+        double* base = reinterpret_cast<double*>(p.out);
+        const bool vec = ((p.ldo & 1) == 0) && ((reinterpret_cast<uintptr_t>(base) & 15) == 0);
+        double sc0 = 1.0, sc1 = 1.0;
+        if (norm) {
+            if (ok >= 1) sc0 = p.sd_cols[col];
+            if (ok == 2) sc1 = p.sd_cols[col + 1];
+        }
+#pragma unroll 4
+        for (int r2 = 0; r2 < 16; ++r2) {
+            const int rr = 2 * r2 + half;
+            const uint2 iv = *reinterpret_cast<const uint2*>(stage + rr * 32 + (((l16 >> 1) ^ (rr & 7)) << 2) + ((l16 & 1) << 1));
+            if (rr < nrow && ok) {
+                double d0 = u32_to_f64<INT_CVT>(iv.x), d1 = u32_to_f64<INT_CVT>(iv.y);
+                if (norm) {
+                    // normalize_K (kernels.py:408-414): K_ij / (sqrt(K_ii) * sqrt(K_jj)), diagonal := 1.0
+                    const double sr = p.sd_rows[row_base + rr];
+                    const int64_t grow = p.row_index0 + row_base + rr, gcol = p.col_index0 + col;
+                    d0 = __ddiv_rn(d0, __dmul_rn(sr, sc0));
+                    d1 = __ddiv_rn(d1, __dmul_rn(sr, sc1));
+                    if (grow == gcol) d0 = 1.0;
+                    if (grow == gcol + 1) d1 = 1.0;
                 }
+                double* dst = base + (row_base + rr) * p.ldo + col;
+                if (ok == 2 && vec) *reinterpret_cast<double2*>(dst) = make_double2(d0, d1);
+                else { dst[0] = d0; if (ok == 2) dst[1] = d1; }
             }
         }
+        const int64_t row_t = row_base + lane;
         if (mirror && row_t < p.rows) {
             double* dt = reinterpret_cast<double*>(p.out_t) + col0 * p.ldo_t + row_t;
             const double sr = norm ? p.sd_rows[row_t] : 1.0;
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
                 if (j < ncol) {
-                    double val = (double)(int32_t)v[j];
+                    double val = u32_to_f64<INT_CVT>(v[j]);
                     if (norm) val = __ddiv_rn(val, __dmul_rn(sr, p.sd_cols[col0 + j]));  // mirrored tiles never contain the diagonal
                     dt[(int64_t)j * p.ldo_t] = val;
                 }
@@ -139,7 +181,8 @@ gram_i8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                        const KernelParams p) {
     using C = Cfg<M_SUB>;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // 1024-B alignment by offsetting the __shared__ symbol (keeps the address space known to the compiler: LDS/STS, not generic LD/ST)
+    uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
     uint64_t* empty = full + C::STAGES;
     uint64_t* tfull = empty + C::STAGES;
@@ -198,8 +241,12 @@ gram_i8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                     }
                 }
                 for (int kb = 0; kb < p.kblocks; ++kb) {
+                    if (p.prefetch_dist > 0 && kb + p.prefetch_dist < p.kblocks) {
+                        ptx::tma_prefetch_2d(&tmA, (kb + p.prefetch_dist) * BK, row0);
+                        ptx::tma_prefetch_2d(&tmB, (kb + p.prefetch_dist) * BK, col0);
+                    }
                     ptx::mbar_wait(&empty[stage], phase ^ 1);
-                    ptx::mbar_arrive_expect_tx(&full[stage], C::STAGE_BYTES);
+                    ptx::mbar_arrive_expect_tx(&full[stage], p.dbg_b_bytes ? C::A_BYTES + p.dbg_b_bytes : C::STAGE_BYTES);
                     uint8_t* sa = smem + stage * C::STAGE_BYTES;
                     ptx::tma_load_2d_hint(sa, &tmA, &full[stage], kb * BK, row0, p.hint_a);
                     ptx::tma_load_2d_hint(sa + C::A_BYTES, &tmB, &full[stage], kb * BK, col0, p.hint_b);
@@ -261,7 +308,7 @@ gram_i8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                     uint32_t v[32];
                     ptx::tmem_ld_32x32b_x32(taddr, v);
                     ptx::tmem_ld_wait();
-                    store_chunk(p, v, epi_stage + (warp - 4) * C::EPI_STAGE_WORDS, lane, row_base, col0, mirror);
+                    store_chunk<false>(p, v, epi_stage + (warp - 4) * C::EPI_STAGE_WORDS, lane, row_base, col0, mirror);
                 }
             }
             ptx::tcgen05_fence_before();
@@ -275,6 +322,162 @@ gram_i8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     if (warp == 2) {
         ptx::tcgen05_fence_after();
         ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// CTA-pair variant (cta_group::2): two SMs of one TPC compute one 256 x 256 tile.  Each CTA holds 128 rows of A and
+// 128 of the 256 rows of B per stage (32 KB, so 6 stages fit) and 128 x 256 accumulators in its TMEM -- two
+// accumulator stages fit, so the epilogue (bounded by the ~64 B/clk/SM store path: 256 KB per CTA and tile) runs
+// under the next tile's main loop instead of in series with it.  The leader CTA's single MMA thread issues
+// tcgen05.mma.cta_group::2 (M = 256); both CTAs' TMA loads credit the leader's `full` barrier; the MMA completion
+// is multicast to both CTAs' `empty` / `tmem_full` barriers; both CTAs' epilogue warps arrive on the leader's
+// `tmem_empty` barrier.
+// ---------------------------------------------------------------------------------------------
+struct Cfg2 {
+    static constexpr int BM = 256;        // pair tile rows (128 per CTA)
+    static constexpr int STAGES = 6;
+    static constexpr int ACC_STAGES = 2;
+    static constexpr int ACC_COLS = 256;
+    static constexpr uint32_t A_BYTES = 128 * BK;
+    static constexpr uint32_t B_BYTES = 128 * BK;
+    static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr uint32_t EPI_STAGE_WORDS = 32 * 32;
+    static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + NUM_EPI_WARPS * EPI_STAGE_WORDS * 4;
+};
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gram_i8_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const KernelParams p) {
+    using C = Cfg2;
+    extern __shared__ uint8_t smem_raw[];
+    // 1024-B alignment by offsetting the __shared__ symbol (keeps the address space known to the compiler: LDS/STS, not generic LD/ST)
+    uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+    uint64_t* empty = full + C::STAGES;
+    uint64_t* tfull = empty + C::STAGES;
+    uint64_t* tempty = tfull + C::ACC_STAGES;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + C::ACC_STAGES);
+    uint32_t* epi_stage = reinterpret_cast<uint32_t*>(smem + C::STAGES * C::STAGE_BYTES + 256);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = ptx::cluster_ctarank();  // 0 = leader
+    const int cluster_id = blockIdx.x >> 1;
+    const int num_clusters = gridDim.x >> 1;
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tensormap(&tmA);
+        ptx::prefetch_tensormap(&tmB);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < C::STAGES; ++s) {
+            ptx::mbar_init(&full[s], 1);    // leader: its own arrive.expect_tx for the bytes of both CTAs
+            ptx::mbar_init(&empty[s], 1);   // multicast tcgen05.commit
+        }
+        for (int a = 0; a < C::ACC_STAGES; ++a) {
+            ptx::mbar_init(&tfull[a], 1);                    // multicast tcgen05.commit
+            ptx::mbar_init(&tempty[a], 2 * NUM_EPI_WARPS);   // leader: epilogue warps of both CTAs
+        }
+        ptx::fence_barrier_init();
+    }
+    if (warp == 2) {
+        ptx::tmem_alloc_2cta(tmem_slot, TMEM_COLS);
+        ptx::tmem_relinquish_2cta();
+    }
+    ptx::tcgen05_fence_before();
+    ptx::cluster_sync_all();
+    ptx::tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------ TMA producer (both CTAs)
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0, wave = 0;
+            for (int t = cluster_id; t < p.ntiles; t += num_clusters, ++wave) {
+                const int4 tile = p.tiles[t];
+                const int32_t row0 = tile.x * C::BM + (int)rank * 128, col0 = tile.y * BN + (int)rank * 128;
+                if (p.wave_counter != nullptr) {  // see gram_i8_tcgen05_kernel: all CTAs start their w-th tile together
+                    ptx::red_release_gpu_add(p.wave_counter, 1u);
+                    const uint32_t done = (wave + 1) * gridDim.x;
+                    const uint32_t target = done < 2u * (uint32_t)p.ntiles ? done : 2u * (uint32_t)p.ntiles;
+                    if (ptx::ld_acquire_gpu(p.wave_counter) < target) {
+                        const uint64_t t0 = ptx::globaltimer_ns();
+                        while (ptx::ld_acquire_gpu(p.wave_counter) < target) {
+                            __nanosleep(200);
+                            if (ptx::globaltimer_ns() - t0 > 4000000000ull) __trap();
+                        }
+                    }
+                }
+                for (int kb = 0; kb < p.kblocks; ++kb) {
+                    ptx::mbar_wait(&empty[stage], phase ^ 1);
+                    if (rank == 0) ptx::mbar_arrive_expect_tx(&full[stage], 2 * C::STAGE_BYTES);
+                    uint8_t* sa = smem + stage * C::STAGE_BYTES;
+                    ptx::tma_load_2d_2cta(sa, &tmA, &full[stage], kb * BK, row0, p.hint_a);
+                    ptx::tma_load_2d_2cta(sa + C::A_BYTES, &tmB, &full[stage], kb * BK, col0, p.hint_b);
+                    if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ------------------------------------------------------------ MMA issuer (leader CTA only)
+        if (lane == 0 && rank == 0) {
+            constexpr uint32_t idesc = ptx::make_idesc_i8(256, BN);
+            uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+            for (int t = cluster_id; t < p.ntiles; t += num_clusters) {
+                ptx::mbar_wait(&tempty[acc], acc_phase ^ 1);
+                ptx::tcgen05_fence_after();
+                for (int kb = 0; kb < p.kblocks; ++kb) {
+                    ptx::mbar_wait(&full[stage], phase);
+                    ptx::tcgen05_fence_after();
+                    const uint32_t a_addr = ptx::smem_u32(smem + stage * C::STAGE_BYTES);
+                    const uint32_t b_addr = a_addr + C::A_BYTES;
+#pragma unroll
+                    for (int k4 = 0; k4 < BK / UMMA_K; ++k4) {
+                        const uint64_t adesc = ptx::make_smem_desc_kmajor_sw128(a_addr + k4 * UMMA_K);
+                        const uint64_t bdesc = ptx::make_smem_desc_kmajor_sw128(b_addr + k4 * UMMA_K);
+                        ptx::umma_i8_2cta(tmem_base + acc * C::ACC_COLS, adesc, bdesc, idesc, (kb | k4) != 0 ? 1u : 0u);
+                    }
+                    ptx::umma_commit_2cta(&empty[stage], 3);  // both CTAs may refill this stage
+                    if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                }
+                ptx::umma_commit_2cta(&tfull[acc], 3);  // both CTAs' epilogues
+                if (++acc == C::ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+        __syncwarp();
+    } else if (warp >= 4) {
+        // ------------------------------------------------------------ epilogue (both CTAs, own 128 rows)
+        const int quarter = warp & 3;
+        const int half = (warp - 4) >> 2;
+        uint32_t acc = 0, acc_phase = 0;
+        for (int t = cluster_id; t < p.ntiles; t += num_clusters) {
+            const int4 tile = p.tiles[t];
+            const bool mirror = tile.z != 0;
+            ptx::mbar_wait(&tfull[acc], acc_phase);
+            ptx::tcgen05_fence_after();
+            const int64_t row_base = (int64_t)tile.x * C::BM + (int64_t)rank * 128 + quarter * 32;
+#pragma unroll 1
+            for (int ch = 0; ch < 4; ++ch) {
+                const int64_t col0 = (int64_t)tile.y * BN + half * 128 + ch * 32;
+                if (col0 >= p.cols) break;  // warp-uniform
+                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * C::ACC_COLS + half * 128 + ch * 32;
+                uint32_t v[32];
+                ptx::tmem_ld_32x32b_x32(taddr, v);
+                ptx::tmem_ld_wait();
+                store_chunk<true>(p, v, epi_stage + (warp - 4) * C::EPI_STAGE_WORDS, lane, row_base, col0, mirror);
+            }
+            ptx::tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive_cluster(&tempty[acc], 0);  // the leader's MMA thread waits on it
+            if (++acc == C::ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+    ptx::tcgen05_fence_before();
+    ptx::cluster_sync_all();
+    if (warp == 2) {
+        ptx::tcgen05_fence_after();
+        ptx::tmem_dealloc_2cta(tmem_base, TMEM_COLS);
     }
 }
 
@@ -427,6 +630,32 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const KernelParams& p
     return KMG_OK;
 }
 
+int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const KernelParams& p, int sms, cudaStream_t stream) {
+    static bool attr_set[64] = {};
+    int dev = 0;
+    KMG_CUDA_CHECK(cudaGetDevice(&dev));
+    if (!attr_set[dev & 63]) {
+        KMG_CUDA_CHECK(cudaFuncSetAttribute(gram_i8_2cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg2::SMEM_BYTES));
+        attr_set[dev & 63] = true;
+    }
+    int clusters = sms / 2;
+    if (p.ntiles < clusters) clusters = p.ntiles;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * clusters);
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = Cfg2::SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    KMG_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gram_i8_2cta_kernel, tmA, tmB, p));
+    return KMG_OK;
+}
+
 }  // namespace
 
 int kmg_gram_i8_launch(const GramI8Args* a, cudaStream_t stream) {
@@ -439,18 +668,22 @@ int kmg_gram_i8_launch(const GramI8Args* a, cudaStream_t stream) {
     KMG_REQUIRE(a->rows < (1ll << 31) && a->cols < (1ll << 31), KMG_ERR_ARG, "gram_i8: block too large");
     KMG_REQUIRE(!a->symmetric || a->out_t != nullptr, KMG_ERR_ARG, "gram_i8: symmetric needs a mirror destination");
     int m_sub = a->m_sub;
-    if (m_sub == 0) m_sub = (a->Dpad >= 2048) ? 2 : 1;
-    KMG_REQUIRE(m_sub == 1 || m_sub == 2, KMG_ERR_ARG, "gram_i8: m_sub must be 0, 1 or 2");
-    const int BM = 128 * m_sub;
+    static const int default_variant = env_int("KMG_GEMM_VARIANT", 0);
+    if (m_sub == 0) m_sub = default_variant;
+    if (m_sub == 0) m_sub = 3;  // the CTA-pair kernel is the fastest variant at every measured shape
+    KMG_REQUIRE(m_sub >= 1 && m_sub <= 3, KMG_ERR_ARG, "gram_i8: m_sub must be 0 (auto), 1, 2 or 3 (CTA pair)");
+    const bool pair = m_sub == 3;
+    const int BM = pair ? 256 : 128 * m_sub;
     int dev = 0, sms = 0;
     KMG_CUDA_CHECK(cudaGetDevice(&dev));
     KMG_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     if (a->max_ctas > 0 && a->max_ctas < sms) sms = a->max_ctas;
 
     CUtensorMap tmA, tmB;
-    int rc = make_map(&tmA, a->phi_rows, a->rows, a->Dpad, a->ld_phi, BM);
+    int rc = make_map(&tmA, a->phi_rows, a->rows, a->Dpad, a->ld_phi, pair ? 128 : BM);
     if (rc) return rc;
-    rc = make_map(&tmB, a->phi_cols, a->cols, a->Dpad, a->ld_phi, BN);
+    static const int dbg_half_b = env_int("KMG_GEMM_DBG_HALFB", 0);  // timing experiment: load only 128 of the 256 B rows (results wrong)
+    rc = make_map(&tmB, a->phi_cols, a->cols, a->Dpad, a->ld_phi, (dbg_half_b || pair) ? 128 : BN);
     if (rc) return rc;
 
     static const int band = env_int("KMG_GEMM_BAND", 8);
@@ -474,12 +707,19 @@ int kmg_gram_i8_launch(const GramI8Args* a, cudaStream_t stream) {
     p.sd_rows = a->sd_rows; p.sd_cols = a->sd_cols;
     p.tiles = tl.dev;
     p.wave_counter = nullptr;
-    if (sync_waves && tl.n > sms) {
+    // the wave barrier only pays when the operands do not stay in L2 on their own (126 MB, two partitions)
+    // one wave touches ~27 operand panels of 256 rows x Dpad bytes: below ~8 KB of features per row they all sit in L2
+    const bool spills_l2 = a->Dpad >= 8192 && (double)(a->rows + a->cols) * (double)a->Dpad > 96e6;
+    if (sync_waves && spills_l2 && tl.n > (pair ? sms / 2 : sms)) {
         rc = get_counter(stream, &p.wave_counter);
         if (rc) return rc;
     }
     p.hint_a = hint_mode == 1 ? ptx::L2_EVICT_LAST : ptx::L2_EVICT_NORMAL;
     p.hint_b = hint_mode == 2 ? ptx::L2_EVICT_FIRST : ptx::L2_EVICT_NORMAL;
+    p.dbg_b_bytes = dbg_half_b ? 128 * BK : 0;
+    static const int pf = env_int("KMG_GEMM_PF", 0);
+    p.prefetch_dist = pf;
+    if (pair) return launch_pair(tmA, tmB, p, sms, stream);
     return m_sub == 1 ? launch<1>(tmA, tmB, p, sms, stream) : launch<2>(tmA, tmB, p, sms, stream);
 }
 

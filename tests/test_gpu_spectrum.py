@@ -66,7 +66,7 @@ def test_spectrum_phi_matches_oracle(kd, dna):
         assert not phi[:, D:].any()
 
 
-@pytest.mark.parametrize("m_sub", [1, 2])
+@pytest.mark.parametrize("m_sub", [1, 2, 3])
 def test_gram_tcgen05_vs_oracle_small(kd, dna, m_sub):
     """Known answers: real rows, every k, both tile shapes, s32 and f64 outputs, ragged n."""
     codes, _ = dna
@@ -93,7 +93,7 @@ def test_gram_golden_vectors(kd, golden, dna):
         assert np.array_equal(got, golden[name]), name
 
 
-@pytest.mark.parametrize("m_sub", [1, 2])
+@pytest.mark.parametrize("m_sub", [1, 2, 3])
 def test_gram_tcgen05_vs_simt_medium(kd, m_sub):
     """n = 3000 synthetic, D = 21 844: the tcgen05 kernel against an independent dp4a evaluation on device,
     plus block-row / cross-block launches against slices of the same matrix."""

@@ -54,9 +54,9 @@ def main():
                 continue
             phi = kd.spectrum_phi(planes, 101, ks)
             W = phi.shape[1]
-            for m_sub in (1, 2):
+            for m_sub in (1, 2, 3):
                 for dt in (0, 1):
-                    if args.quick and (m_sub, dt) != (2, 1):
+                    if args.quick and (m_sub, dt) not in ((2, 1), (3, 1)):
                         continue
                     out = torch.empty((n, cols), dtype=torch.float64 if dt else torch.int32, device="cuda")
                     med, best = timeit(lambda: kd.gram_i8(phi[:n], phi[:cols], out_dtype=dt, m_sub=m_sub, out=out))

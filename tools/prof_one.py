@@ -1,0 +1,38 @@
+"""prof_one.py -- run one kernel configuration a few times (target for ncu)."""
+import argparse, os, sys
+import numpy as np, torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (os.path.join(ROOT, "kernel-methods-for-genomics_b200"), os.path.join(ROOT, "oracle")):
+    sys.path.insert(0, p)
+from kmg import device as kd
+import oracle_np as onp
+ap = argparse.ArgumentParser()
+ap.add_argument("--kind", default="gemm")
+ap.add_argument("--rows", type=int, default=16384)
+ap.add_argument("--cols", type=int, default=16384)
+ap.add_argument("--ks", default="6")
+ap.add_argument("--m_sub", type=int, default=3)
+ap.add_argument("--dt", type=int, default=1)
+ap.add_argument("--iters", type=int, default=3)
+a = ap.parse_args()
+n = max(a.rows, a.cols)
+planes = kd.pack(onp.synthetic_codes(n, 101, seed=3), 0)
+if a.kind == "gemm":
+    ks = [int(x) for x in a.ks.split(",")]
+    phi = kd.spectrum_phi(planes, 101, ks)
+    out = torch.empty((a.rows, a.cols), dtype=torch.float64 if a.dt else torch.int32, device="cuda")
+    fn = lambda: kd.gram_i8(phi[:a.rows], phi[:a.cols], out_dtype=a.dt, m_sub=a.m_sub, out=out)
+elif a.kind == "wd":
+    out = torch.empty((a.rows, a.cols), dtype=torch.float64, device="cuda")
+    fn = lambda: kd.wd_block(planes[:a.rows], planes[:a.cols], 101, 10, out=out)
+elif a.kind == "mm":
+    out = torch.empty((a.rows, a.cols), dtype=torch.float64, device="cuda")
+    fn = lambda: kd.mismatch_block(planes[:a.rows], planes[:a.cols], 101, 10, 1, out=out)
+elif a.kind == "la":
+    out = torch.empty((a.rows, a.cols), dtype=torch.float64, device="cuda")
+    fn = lambda: kd.la_block(planes[:a.rows], planes[:a.cols], 101, 11, 1, 0.5, 0, out=out)
+ts = []
+for _ in range(a.iters):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); fn(); e1.record(); torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1))
+print(a.kind, a.rows, a.cols, "ms:", ["%.3f" % t for t in ts])
