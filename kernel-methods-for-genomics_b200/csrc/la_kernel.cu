@@ -1,4 +1,4 @@
-// la_kernel.cu -- Vert-Saigo local-alignment kernel, anti-diagonal wavefront DP, one warp per pair.
+// la_kernel.cu -- Vert-Saigo local-alignment kernel, anti-diagonal wavefront DP in registers.
 //
 // Reference: affine_align / Smith_Waterman / get_LA_K (kernels.py:226-302).  AS WRITTEN the
 // reference returns exactly 0.0 for every pair (its five DP matrices are one aliased array,
@@ -13,17 +13,20 @@
 //   Y2[i,j] = M[i,j-1] + X2[i,j-1] + Y2[i,j-1]
 //   K(x,y)  = (1/b) ln(1 + X2 + Y2 + M)[n_x, n_y]
 //
-// Lane l owns rows 4l+1..4l+4 and walks the columns skewed by one step per lane (lane l is on
-// column t-l+1 at step t), so the warp sweeps anti-diagonal bands; the row above a lane's strip
-// arrives by __shfl_up from the lane that computed it one step earlier.
+// A group of LP lanes (16 or 32) owns one pair; lane l owns rows l*RPL+1 .. l*RPL+RPL and walks the
+// columns skewed by one step per lane (lane l is on column t-l at step t), so the group sweeps
+// anti-diagonal bands; the row above a lane's strip arrives by __shfl_up from the lane that computed
+// it one step earlier.  For the challenge's L = 101 two pairs share a warp (16 lanes x 7 rows):
+// 116 steps of 7 cells per lane instead of 132 steps of 4 cells with 6 lanes idle.
 //
 // Numerics: with the reference's default parameters (e=11, d=1, beta=0.5, taken literally as
 // e^{+b e}) the linear-space values overflow fp64 within ~90 cells, so the state is kept in fp64
-// scaled by a warp-wide power of two 2^-E: whenever the largest live value exceeds 2^64 every live
-// value is multiplied by an exact power of two and E is bumped (error-free).  The result is
-// (ln(sum_scaled) + E ln 2)/b.  This is mathematically the log-space evaluation the north star
-// asks for at ~1/50th of the flops of a literal log-sum-exp per cell.  Smith-Waterman (max-plus)
-// runs directly in log space (adds and maxes only).
+// scaled by a group-wide power of two 2^-E: whenever the largest live value exceeds 2^64 every live
+// value is multiplied by an exact power of two and E is bumped (error-free).  The check runs every
+// `check_every` steps, chosen on the host from the worst-case growth per step so that nothing can
+// overflow in between.  The result is (ln(sum_scaled) + E ln 2)/b -- mathematically the log-space
+// evaluation the north star asks for at ~1/50th of the flops of a literal log-sum-exp per cell.
+// Smith-Waterman (max-plus) runs directly in log space (adds and maxes only).
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
@@ -34,12 +37,12 @@
 
 namespace {
 
-constexpr int LA_WARPS = 8;
-constexpr int ROWS_PER_LANE = 4;
+constexpr int LA_THREADS = 256;
 
 struct LaParams {
     int L;
     int smith;
+    int check_every;    // steps between rescale checks (affine)
     double inv_beta;
     double ed, ee;      // e^{beta d}, e^{beta e}    (affine)
     double bd, be;      // beta d, beta e            (smith)
@@ -60,60 +63,68 @@ __device__ __forceinline__ int code_at(const SeqPlanes& s, int pos) {
     return (int)(((lo >> b) & 1u) | (((hi >> b) & 1u) << 1));
 }
 
-__device__ __forceinline__ double shfl_up_d(double v) { return __shfl_up_sync(0xffffffffu, v, 1); }
+template <int LP>
+__device__ __forceinline__ double shfl_up_d(unsigned mask, double v) { return __shfl_up_sync(mask, v, 1, LP); }
 
-__global__ void __launch_bounds__(LA_WARPS * 32)
+template <int LP, int RPL>
+__global__ void __launch_bounds__(LA_THREADS)
 la_kernel(const uint32_t* __restrict__ prow, const uint32_t* __restrict__ pcol, const LaParams p) {
-    __shared__ uint8_t ycode_s[LA_WARPS][KMG_MAX_L];
+    constexpr int GROUPS = LA_THREADS / LP;  // pairs per CTA
+    __shared__ uint8_t ycode_s[GROUPS][KMG_MAX_L];
     __shared__ double sub_s[16];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int group = threadIdx.x / LP, gl = threadIdx.x % LP;  // group in CTA, lane in group
+    const unsigned gmask = (LP == 32) ? 0xffffffffu : (0xffffu << (16 * ((threadIdx.x & 31) >> 4)));
     if (threadIdx.x < 16) sub_s[threadIdx.x] = p.sub[threadIdx.x];
     __syncthreads();
-    const int64_t pair = (int64_t)blockIdx.x * LA_WARPS + warp;
-    if (pair >= p.rows * p.cols) return;
+    int64_t pair = (int64_t)blockIdx.x * GROUPS + group;
+    const int64_t npairs = p.rows * p.cols;
+    const bool in_range = pair < npairs;
+    if (!in_range) pair = npairs - 1;  // keep the half-warp alive for the collectives; its result is not stored
     const int64_t r = pair / p.cols, c = pair % p.cols;
     const int64_t gr = p.row_index0 + r, gc = p.col_index0 + c;
-    if (p.symmetric && gc < gr) return;  // produced by the mirror store of (c, r)
+    const bool skip = p.symmetric && gc < gr;  // produced by the mirror store of (c, r)
+    // a whole warp whose groups have nothing to do can leave (warp-uniform test)
+    if (__all_sync(0xffffffffu, skip || !in_range)) return;
     // kernels.py:289-291: K[i,j] is evaluated with x = row i, y = row j for j >= i, then mirrored
     const bool swap = gc < gr;
     const SeqPlanes xs = swap ? kmg_load_planes(pcol, c) : kmg_load_planes(prow, r);
     const SeqPlanes ys = swap ? kmg_load_planes(prow, r) : kmg_load_planes(pcol, c);
     const int L = p.L;
-    for (int j = lane; j < KMG_MAX_L; j += 32) ycode_s[warp][j] = (uint8_t)code_at(ys, j);
+    for (int j = gl; j < KMG_MAX_L; j += LP) ycode_s[group][j] = (uint8_t)code_at(ys, j);
     __syncwarp();
-    int xc[ROWS_PER_LANE];
+    int xc[RPL];
 #pragma unroll
-    for (int q = 0; q < ROWS_PER_LANE; ++q) xc[q] = code_at(xs, (lane * ROWS_PER_LANE + q) & 127) << 2;
+    for (int q = 0; q < RPL; ++q) xc[q] = code_at(xs, (gl * RPL + q) & 127) << 2;
 
-    const int last_lane = (L - 1) / ROWS_PER_LANE, last_q = (L - 1) % ROWS_PER_LANE;
-    const int steps = L + 31;
+    const int last_lane = (L - 1) / RPL, last_q = (L - 1) % RPL;
+    const int steps = L + LP - 1;
     double result = 0.0;
 
     if (!p.smith) {
         // ---------------- affine_align, scaled linear space
-        double M[ROWS_PER_LANE], X[ROWS_PER_LANE], Y[ROWS_PER_LANE], X2[ROWS_PER_LANE], Y2[ROWS_PER_LANE];
+        double M[RPL], X[RPL], Y[RPL], X2[RPL], Y2[RPL];
 #pragma unroll
-        for (int q = 0; q < ROWS_PER_LANE; ++q) M[q] = X[q] = Y[q] = X2[q] = Y2[q] = 0.0;
+        for (int q = 0; q < RPL; ++q) M[q] = X[q] = Y[q] = X2[q] = Y2[q] = 0.0;
         double dM = 0.0, dX = 0.0, dY = 0.0;  // row above the strip, previous column
         int E = 0;                            // stored = true * 2^-E
         double one_s = 1.0;
         const double ed = p.ed, ee = p.ee;
+        int until_check = p.check_every;
 #pragma unroll 1
         for (int t = 0; t < steps; ++t) {
             // bottom row of the lane above, as computed in the previous step (= this lane's column j)
-            double uM = shfl_up_d(M[ROWS_PER_LANE - 1]);
-            double uX = shfl_up_d(X[ROWS_PER_LANE - 1]);
-            double uY = shfl_up_d(Y[ROWS_PER_LANE - 1]);
-            double uX2 = shfl_up_d(X2[ROWS_PER_LANE - 1]);
-            if (lane == 0) uM = uX = uY = uX2 = 0.0;
-            const int j = t - lane;  // 0-based column
-            const bool active = j >= 0 && j < L;
-            if (active) {
-                const int yc = ycode_s[warp][j];
-                double aM = uM, aX = uX, aY = uY, aX2 = uX2;  // "up"   : (i-1, j)
-                double gM = dM, gX = dX, gY = dY;             // "diag" : (i-1, j-1)
+            double uM = shfl_up_d<LP>(gmask, M[RPL - 1]);
+            double uX = shfl_up_d<LP>(gmask, X[RPL - 1]);
+            double uY = shfl_up_d<LP>(gmask, Y[RPL - 1]);
+            double uX2 = shfl_up_d<LP>(gmask, X2[RPL - 1]);
+            if (gl == 0) uM = uX = uY = uX2 = 0.0;
+            const int j = t - gl;  // 0-based column
+            if (j >= 0 && j < L) {
+                const int yc = ycode_s[group][j];
+                double aM = uM, aX = uX, aX2 = uX2;  // "up"   : (i-1, j)
+                double gM = dM, gX = dX, gY = dY;    // "diag" : (i-1, j-1)
 #pragma unroll
-                for (int q = 0; q < ROWS_PER_LANE; ++q) {
+                for (int q = 0; q < RPL; ++q) {
                     const double a = sub_s[xc[q] | yc];
                     const double lM = M[q], lX = X[q], lY = Y[q], lX2 = X2[q], lY2 = Y2[q];  // "left": (i, j-1)
                     const double nM = a * (((one_s + gX) + gY) + gM);
@@ -122,67 +133,68 @@ la_kernel(const uint32_t* __restrict__ prow, const uint32_t* __restrict__ pcol, 
                     const double nX2 = aM + aX2;
                     const double nY2 = (lM + lX2) + lY2;
                     gM = lM; gX = lX; gY = lY;
-                    aM = nM; aX = nX; aY = nY; aX2 = nX2;
+                    aM = nM; aX = nX; aX2 = nX2;
                     M[q] = nM; X[q] = nX; Y[q] = nY; X2[q] = nX2; Y2[q] = nY2;
                 }
-                (void)aY;
                 dM = uM; dX = uX; dY = uY;
             }
-            if (t == L - 1 + last_lane && lane == last_lane) {
+            if (t == L - 1 + last_lane && gl == last_lane) {
                 // cell (n_x, n_y): this lane's row last_q at column L-1
                 double m = M[0], x2 = X2[0], y2 = Y2[0];
 #pragma unroll
-                for (int q = 1; q < ROWS_PER_LANE; ++q)
+                for (int q = 1; q < RPL; ++q)
                     if (q == last_q) { m = M[q]; x2 = X2[q]; y2 = Y2[q]; }
                 const double tot = ((one_s + x2) + y2) + m;
                 result = p.inv_beta * (log(tot) + (double)E * 0.6931471805599453094);
             }
-            // ---- warp-wide power-of-two rescale (exact)
-            int hi = 0;
+            if (--until_check == 0) {
+                until_check = p.check_every;
+                // ---- group-wide power-of-two rescale (exact)
+                int hi = 0;
 #pragma unroll
-            for (int q = 0; q < ROWS_PER_LANE; ++q) {
-                hi = max(hi, __double2hiint(M[q]));
-                hi = max(hi, __double2hiint(X[q]));
-                hi = max(hi, __double2hiint(Y[q]));
-                hi = max(hi, __double2hiint(X2[q]));
-                hi = max(hi, __double2hiint(Y2[q]));
-            }
-            hi = __reduce_max_sync(0xffffffffu, hi);
-            const int ex = (hi >> 20) - 1023;  // exponent of the largest live value (all values >= 0)
-            if (ex > 64) {                     // warp-uniform
-                const double sc = __hiloint2double((1023 - ex) << 20, 0);  // 2^-ex
-#pragma unroll
-                for (int q = 0; q < ROWS_PER_LANE; ++q) {
-                    M[q] *= sc; X[q] *= sc; Y[q] *= sc; X2[q] *= sc; Y2[q] *= sc;
+                for (int q = 0; q < RPL; ++q) {
+                    hi = max(hi, __double2hiint(M[q]));
+                    hi = max(hi, __double2hiint(X[q]));
+                    hi = max(hi, __double2hiint(Y[q]));
+                    hi = max(hi, __double2hiint(X2[q]));
+                    hi = max(hi, __double2hiint(Y2[q]));
                 }
-                dM *= sc; dX *= sc; dY *= sc;
-                E += ex;
-                one_s = (E < 1000) ? __hiloint2double((1023 - E) << 20, 0) : 0.0;  // 2^-E (negligible beyond)
+                hi = __reduce_max_sync(gmask, hi);
+                const int ex = (hi >> 20) - 1023;  // exponent of the largest live value (all values >= 0)
+                if (ex > 64) {                     // uniform within the group
+                    const double sc = __hiloint2double((1023 - ex) << 20, 0);  // 2^-ex
+#pragma unroll
+                    for (int q = 0; q < RPL; ++q) {
+                        M[q] *= sc; X[q] *= sc; Y[q] *= sc; X2[q] *= sc; Y2[q] *= sc;
+                    }
+                    dM *= sc; dX *= sc; dY *= sc;
+                    E += ex;
+                    one_s = (E < 1000) ? __hiloint2double((1023 - E) << 20, 0) : 0.0;  // 2^-E (negligible beyond)
+                }
             }
         }
     } else {
         // ---------------- Smith_Waterman (max-plus), log space
         const double NI = -INFINITY;
-        double M[ROWS_PER_LANE], X[ROWS_PER_LANE], Y[ROWS_PER_LANE], X2[ROWS_PER_LANE], Y2[ROWS_PER_LANE];
+        double M[RPL], X[RPL], Y[RPL], X2[RPL], Y2[RPL];
 #pragma unroll
-        for (int q = 0; q < ROWS_PER_LANE; ++q) M[q] = X[q] = Y[q] = X2[q] = Y2[q] = NI;
+        for (int q = 0; q < RPL; ++q) M[q] = X[q] = Y[q] = X2[q] = Y2[q] = NI;
         double dM = NI, dX = NI, dY = NI;
         const double bd = p.bd, be = p.be;
 #pragma unroll 1
         for (int t = 0; t < steps; ++t) {
-            double uM = shfl_up_d(M[ROWS_PER_LANE - 1]);
-            double uX = shfl_up_d(X[ROWS_PER_LANE - 1]);
-            double uY = shfl_up_d(Y[ROWS_PER_LANE - 1]);
-            double uX2 = shfl_up_d(X2[ROWS_PER_LANE - 1]);
-            if (lane == 0) uM = uX = uY = uX2 = NI;
-            const int j = t - lane;
-            const bool active = j >= 0 && j < L;
-            if (active) {
-                const int yc = ycode_s[warp][j];
+            double uM = shfl_up_d<LP>(gmask, M[RPL - 1]);
+            double uX = shfl_up_d<LP>(gmask, X[RPL - 1]);
+            double uY = shfl_up_d<LP>(gmask, Y[RPL - 1]);
+            double uX2 = shfl_up_d<LP>(gmask, X2[RPL - 1]);
+            if (gl == 0) uM = uX = uY = uX2 = NI;
+            const int j = t - gl;
+            if (j >= 0 && j < L) {
+                const int yc = ycode_s[group][j];
                 double aM = uM, aX = uX, aX2 = uX2;
                 double gM = dM, gX = dX, gY = dY;
 #pragma unroll
-                for (int q = 0; q < ROWS_PER_LANE; ++q) {
+                for (int q = 0; q < RPL; ++q) {
                     const double s = sub_s[xc[q] | yc];
                     const double lM = M[q], lX = X[q], lY = Y[q], lX2 = X2[q], lY2 = Y2[q];
                     const double nM = s + fmax(fmax(0.0, gX), fmax(gY, gM));
@@ -196,19 +208,30 @@ la_kernel(const uint32_t* __restrict__ prow, const uint32_t* __restrict__ pcol, 
                 }
                 dM = uM; dX = uX; dY = uY;
             }
-            if (t == L - 1 + last_lane && lane == last_lane) {
+            if (t == L - 1 + last_lane && gl == last_lane) {
                 double m = M[0], x2 = X2[0], y2 = Y2[0];
 #pragma unroll
-                for (int q = 1; q < ROWS_PER_LANE; ++q)
+                for (int q = 1; q < RPL; ++q)
                     if (q == last_q) { m = M[q]; x2 = X2[q]; y2 = Y2[q]; }
                 result = p.inv_beta * fmax(fmax(0.0, x2), fmax(y2, m));
             }
         }
     }
-    if (lane == last_lane) {
+    if (gl == last_lane && in_range && !skip) {
         p.out[r * p.ldo + c] = result;
         if (p.symmetric && gc != gr) p.out_t[c * p.ldo_t + r] = result;
     }
+}
+
+template <int LP, int RPL>
+int launch_la(const uint32_t* prow, const uint32_t* pcol, const LaParams& p, cudaStream_t stream) {
+    constexpr int GROUPS = LA_THREADS / LP;
+    const int64_t pairs = p.rows * p.cols;
+    const int64_t blocks = (pairs + GROUPS - 1) / GROUPS;
+    KMG_REQUIRE(blocks < (1ll << 31), KMG_ERR_ARG, "local alignment: block too large for one launch");
+    la_kernel<LP, RPL><<<(unsigned)blocks, LA_THREADS, 0, stream>>>(prow, pcol, p);
+    KMG_CUDA_CHECK(cudaGetLastError());
+    return KMG_OK;
 }
 
 }  // namespace
@@ -220,13 +243,22 @@ int kmg_la_launch(const PairBlock* b, double e, double d, double beta, int smith
     if (b->symmetric)
         KMG_REQUIRE(b->rows == b->cols && b->row_index0 == b->col_index0 && b->out_t != nullptr, KMG_ERR_ARG,
                     "symmetric mode needs a square diagonal block and a mirror destination");
-    // growth per wavefront step is at most (4 rows) * max exponent; keep it far inside the fp64 range
-    const double worst = 4.0 * beta * fmax(fmax(fabs(e), fabs(d)), 9.0) * 1.4427;
-    KMG_REQUIRE(smith || worst < 600.0, KMG_ERR_UNSUPPORTED, "local alignment: beta*max(|e|,|d|,9) too large for the scaled fp64 recursion");
+    const int L = b->L;
+    // lanes per pair / rows per lane: two pairs per warp when 16 x 7 or 16 x 8 rows cover the sequence
+    const int lp = (L > 96) ? 16 : 32;
+    const int rpl = (L > 112) ? 8 : (L > 96 ? 7 : 4);
+    // worst-case growth of any state value per wavefront step, in bits: each of the RPL cells of a lane's column can
+    // multiply by at most 3*max(e^{b s}) or e^{b d} + e^{b e}
+    const double cell_bits = 1.4427 * beta * fmax(fmax(e, d), 9.0) + 2.0;
+    const double step_bits = rpl * fmax(cell_bits, 2.0);
+    KMG_REQUIRE(smith || step_bits < 450.0, KMG_ERR_UNSUPPORTED, "local alignment: beta*max(e,d,9) too large for the scaled fp64 recursion");
     if (b->rows == 0 || b->cols == 0) return KMG_OK;
     static const int S[4][4] = {{4, 0, 0, 0}, {0, 9, -3, -1}, {0, -3, 6, 2}, {0, -1, -2, 5}};  // kernels.py:223
     LaParams p;
-    p.L = b->L; p.smith = smith; p.inv_beta = 1.0 / beta;
+    p.L = L; p.smith = smith; p.inv_beta = 1.0 / beta;
+    // values stay below 2^64 * 2^(check_every * step_bits) < 2^1000 between checks
+    int ce = (int)floor(900.0 / step_bits);
+    p.check_every = ce < 1 ? 1 : (ce > 8 ? 8 : ce);
     p.ed = exp(beta * d); p.ee = exp(beta * e); p.bd = beta * d; p.be = beta * e;
     for (int a = 0; a < 4; ++a)
         for (int c = 0; c < 4; ++c) p.sub[a * 4 + c] = smith ? beta * (double)S[a][c] : exp(beta * (double)S[a][c]);
@@ -234,10 +266,7 @@ int kmg_la_launch(const PairBlock* b, double e, double d, double beta, int smith
     p.symmetric = b->symmetric;
     p.out = reinterpret_cast<double*>(b->out); p.ldo = b->ldo;
     p.out_t = reinterpret_cast<double*>(b->out_t); p.ldo_t = b->ldo_t;
-    const int64_t pairs = b->rows * b->cols;
-    const int64_t blocks = (pairs + LA_WARPS - 1) / LA_WARPS;
-    KMG_REQUIRE(blocks < (1ll << 31), KMG_ERR_ARG, "local alignment: block too large for one launch");
-    la_kernel<<<(unsigned)blocks, LA_WARPS * 32, 0, stream>>>(b->planes_rows, b->planes_cols, p);
-    KMG_CUDA_CHECK(cudaGetLastError());
-    return KMG_OK;
+    if (lp == 16 && rpl == 7) return launch_la<16, 7>(b->planes_rows, b->planes_cols, p, stream);
+    if (lp == 16 && rpl == 8) return launch_la<16, 8>(b->planes_rows, b->planes_cols, p, stream);
+    return launch_la<32, 4>(b->planes_rows, b->planes_cols, p, stream);
 }
