@@ -119,7 +119,7 @@ def cpu_sample_shape(budget_s, oc):
     oc.spectrum_block(codes[:16], codes[:256], KS)
     rate = 16 * 256 / max(time.perf_counter() - t0, 1e-6)  # entries/s incl. feature build (pessimistic)
     cols = 4096
-    rows = int(max(16, min(1024, budget_s * rate * 2 / cols)))
+    rows = int(max(16, min(8192, budget_s * rate * 2 / cols)))
     return rows, cols
 
 
@@ -299,7 +299,7 @@ def main():
         import oracle_c as oc
         oc.build()
         rows, cols = cpu_sample_shape(4.0, oc)
-        v, dtc = run_cpu(rows, cols, 3, 1, oc)
+        v, dtc = run_cpu(rows, cols, 3, 0, oc)
         line["cpu_baseline"] = {"value": v, "unit": "entries/s", "cores": oc.num_threads(), "kind": "port",
                                 "sample": f"{rows} x {cols} entries of the block-row, 3 timed passes of {dtc:.1f} s (oracle/kmg_oracle.c: "
                                           "dense Phi + dot products as kernels.py:12-47, all host threads)"}

@@ -6,6 +6,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <sys/mman.h>
 
 #include <algorithm>
 #include <chrono>
@@ -205,6 +206,13 @@ int d2h_rows(double* dst, int64_t ldk, const double* src, int64_t cols, int64_t 
     int rc = ring_init();
     if (rc) return rc;
     const size_t row_bytes = (size_t)cols * 8;
+    {
+        // Freshly allocated numpy memory is first touched by the copy threads below; with transparent huge pages the
+        // kernel zero-fills 2 MB at a time instead of taking a fault per 4 KB page.  Advisory: errors are ignored.
+        const uintptr_t lo = (reinterpret_cast<uintptr_t>(dst) + 0x1FFFFF) & ~uintptr_t(0x1FFFFF);
+        const uintptr_t hi = (reinterpret_cast<uintptr_t>(dst + (rows - 1) * ldk + cols)) & ~uintptr_t(0x1FFFFF);
+        if (hi > lo) madvise(reinterpret_cast<void*>(lo), hi - lo, MADV_HUGEPAGE);
+    }
     if (row_bytes > D2H_SLOT_BYTES) {  // absurdly wide rows: let the driver stage it
         KMG_CUDA_CHECK(cudaMemcpy2DAsync(dst, (size_t)ldk * 8, src, row_bytes, row_bytes, (size_t)rows, cudaMemcpyDeviceToHost, s));
         KMG_CUDA_CHECK(cudaStreamSynchronize(s));
@@ -225,6 +233,8 @@ int d2h_rows(double* dst, int64_t ldk, const double* src, int64_t cols, int64_t 
         double* d0 = dst + r * ldk;
         fut[slot] = std::async(std::launch::async, [=]() -> int {
             if (cudaEventSynchronize(ev) != cudaSuccess) return 1;
+            static const bool dbg_nocopy = getenv("KMG_DBG_D2H_NOCOPY") != nullptr;  // timing experiment: PCIe leg only
+            if (dbg_nocopy) return 0;
             if (ldk == cols) {
                 memcpy(d0, stage, (size_t)nr * row_bytes);
             } else {
