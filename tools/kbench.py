@@ -68,6 +68,17 @@ def main():
                 out = torch.empty((n, n), dtype=torch.float64, device="cuda")
                 med, best = timeit(lambda: kd.gram_i8(phi[:n], phi[:n], out_dtype=1, symmetric=True, out=out))
                 print(f"gemm ks={ks[0]}..{ks[-1]} W={W} {n}x{n} symmetric f64: {med:.3f} ms  {n * n / med / 1e6:.2f} Gentries/s delivered")
+    if "cublas" in what:
+        # library reference for context only (cuBLASLt int8 IMMA through torch._int_mm, s32 output): not a product path
+        for W in (4096, 21888):
+            a = torch.randint(0, 4, (n, W), dtype=torch.int8, device="cuda")
+            b = torch.randint(0, 4, (W, cols), dtype=torch.int8, device="cuda")
+            try:
+                med, best = timeit(lambda: torch._int_mm(a, b))
+                print(f"cublasLt int8 (torch._int_mm) {n}x{cols}x{W} s32: {med:.3f} ms  {2.0 * n * cols * W / med / 1e9:.1f} TOPS")
+            except Exception as exc:  # noqa: BLE001
+                print("cublasLt int8 unavailable:", exc)
+            del a, b
     if "wd" in what:
         nn = min(n, 32768)
         out = torch.empty((nn, nn), dtype=torch.float64, device="cuda")
