@@ -164,10 +164,12 @@ int pick_block_rows(int64_t nr, int64_t nc, int64_t* block_rows) {
     size_t free_b = 0, total_b = 0;
     KMG_CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
     { std::lock_guard<std::mutex> lk(g_cache.mu); free_b += g_cache.cached_bytes; }  // cached buffers are reclaimable
-    const double budget = 0.70 * (double)free_b;
+    double budget = 0.70 * (double)free_b;
+    if (const char* v = getenv("KMG_DEVICE_BUDGET_BYTES")) budget = atof(v);  // tests force the streamed path at small n
     int64_t r = (int64_t)(budget / (2.0 * 8.0 * (double)std::max<int64_t>(nc, 1)));
     r = std::min<int64_t>(r, 32768);
     r = (r / 256) * 256;
+    if (getenv("KMG_DEVICE_BUDGET_BYTES") && r < 256) r = 256;
     KMG_REQUIRE(r >= 256 || r >= nr, KMG_ERR_NOMEM, "not enough device memory for a 256-row block of %lld columns", (long long)nc);
     *block_rows = std::max<int64_t>(std::min<int64_t>(r, nr), 1);
     return KMG_OK;
@@ -233,8 +235,6 @@ int d2h_rows(double* dst, int64_t ldk, const double* src, int64_t cols, int64_t 
         double* d0 = dst + r * ldk;
         fut[slot] = std::async(std::launch::async, [=]() -> int {
             if (cudaEventSynchronize(ev) != cudaSuccess) return 1;
-            static const bool dbg_nocopy = getenv("KMG_DBG_D2H_NOCOPY") != nullptr;  // timing experiment: PCIe leg only
-            if (dbg_nocopy) return 0;
             if (ldk == cols) {
                 memcpy(d0, stage, (size_t)nr * row_bytes);
             } else {

@@ -54,8 +54,6 @@ struct KernelParams {
     const int4* tiles;  // {row_tile, col_tile, mirror, 0}
     uint32_t* wave_counter;  // grid-wide arrival counter (zeroed before the launch) or null
     uint64_t hint_a, hint_b;  // L2 eviction policy of the A / B operand loads
-    int32_t prefetch_dist;    // k-blocks of L2 prefetch ahead of the smem pipeline (0 = off)
-    uint32_t dbg_b_bytes;     // timing experiment only: bytes of B actually loaded per stage (0 = all)
 };
 
 template <int M_SUB>
@@ -241,12 +239,8 @@ gram_i8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                     }
                 }
                 for (int kb = 0; kb < p.kblocks; ++kb) {
-                    if (p.prefetch_dist > 0 && kb + p.prefetch_dist < p.kblocks) {
-                        ptx::tma_prefetch_2d(&tmA, (kb + p.prefetch_dist) * BK, row0);
-                        ptx::tma_prefetch_2d(&tmB, (kb + p.prefetch_dist) * BK, col0);
-                    }
                     ptx::mbar_wait(&empty[stage], phase ^ 1);
-                    ptx::mbar_arrive_expect_tx(&full[stage], p.dbg_b_bytes ? C::A_BYTES + p.dbg_b_bytes : C::STAGE_BYTES);
+                    ptx::mbar_arrive_expect_tx(&full[stage], C::STAGE_BYTES);
                     uint8_t* sa = smem + stage * C::STAGE_BYTES;
                     ptx::tma_load_2d_hint(sa, &tmA, &full[stage], kb * BK, row0, p.hint_a);
                     ptx::tma_load_2d_hint(sa + C::A_BYTES, &tmB, &full[stage], kb * BK, col0, p.hint_b);
@@ -682,8 +676,7 @@ int kmg_gram_i8_launch(const GramI8Args* a, cudaStream_t stream) {
     CUtensorMap tmA, tmB;
     int rc = make_map(&tmA, a->phi_rows, a->rows, a->Dpad, a->ld_phi, pair ? 128 : BM);
     if (rc) return rc;
-    static const int dbg_half_b = env_int("KMG_GEMM_DBG_HALFB", 0);  // timing experiment: load only 128 of the 256 B rows (results wrong)
-    rc = make_map(&tmB, a->phi_cols, a->cols, a->Dpad, a->ld_phi, (dbg_half_b || pair) ? 128 : BN);
+    rc = make_map(&tmB, a->phi_cols, a->cols, a->Dpad, a->ld_phi, pair ? 128 : BN);
     if (rc) return rc;
 
     static const int band = env_int("KMG_GEMM_BAND", 8);
@@ -716,9 +709,6 @@ int kmg_gram_i8_launch(const GramI8Args* a, cudaStream_t stream) {
     }
     p.hint_a = hint_mode == 1 ? ptx::L2_EVICT_LAST : ptx::L2_EVICT_NORMAL;
     p.hint_b = hint_mode == 2 ? ptx::L2_EVICT_FIRST : ptx::L2_EVICT_NORMAL;
-    p.dbg_b_bytes = dbg_half_b ? 128 * BK : 0;
-    static const int pf = env_int("KMG_GEMM_PF", 0);
-    p.prefetch_dist = pf;
     if (pair) return launch_pair(tmA, tmB, p, sms, stream);
     return m_sub == 1 ? launch<1>(tmA, tmB, p, sms, stream) : launch<2>(tmA, tmB, p, sms, stream);
 }

@@ -91,13 +91,6 @@ __device__ __forceinline__ void tma_load_2d_hint(void* smem_dst, const CUtensorM
         : "memory");
 }
 
-// L2-only prefetch of a tile (no shared-memory destination, no barrier)
-__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* m, int32_t c0, int32_t c1) {
-    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];"
-                 ::"l"(reinterpret_cast<uint64_t>(m)), "r"(c0), "r"(c1)
-                 : "memory");
-}
-
 // grid-wide arrival counter helpers (wave barrier of the persistent GEMM)
 __device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
     uint32_t v;

@@ -115,3 +115,34 @@ def test_spectrum_linearity_over_k(kd):
         total += kd.gram_i8(phi, phi, out_dtype=0).to(torch.int64)
     phi = kd.spectrum_phi(planes, 101, list(range(1, 8)))
     assert torch.equal(kd.gram_i8(phi, phi, out_dtype=0, symmetric=True).to(torch.int64), total)
+
+
+def test_streamed_block_rows_equal_single_launch():
+    """The host API streams row blocks through two device buffers when n x n fp64 exceeds the device budget
+    (n > ~88 000 on a 180 GB B200).  KMG_DEVICE_BUDGET_BYTES forces that path at n = 3000 in a fresh process."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys, numpy as np\n"
+        f"sys.path.insert(0, {os.path.join(root, 'kernel-methods-for-genomics_b200')!r}); sys.path.insert(0, {os.path.join(root, 'oracle')!r})\n"
+        "from kmg import host as kh\nimport oracle_np as onp, oracle_c as oc\n"
+        "c = onp.synthetic_codes(3000, 101, seed=12)\n"
+        "K = kh.spectrum_gram(c, [1, 2, 3, 4, 5, 6, 7])\n"
+        "assert np.array_equal(K, K.T)\n"
+        "assert np.array_equal(K[1000:1016, 2900:3000], oc.spectrum_block(c[1000:1016], c[2900:3000], list(range(1, 8))))\n"
+        "W = kh.wd_gram(c, 10)\n"
+        "assert np.array_equal(W[2990:3000], oc.wd_block(c[2990:3000], c, 10, 2990, 0))\n"
+        "M = kh.mismatch_gram(c[:1500], 10, 1)\n"
+        "assert np.array_equal(M, M.T) and np.all(np.diag(M) == 1.0)\n"
+        "np.save(sys.argv[1], np.array([K.sum(), W.sum(), M.sum()]))\n")
+    outs = []
+    for budget in (None, "48000000"):
+        env = dict(os.environ)
+        if budget:
+            env["KMG_DEVICE_BUDGET_BYTES"] = budget
+        path = os.path.join("/tmp", f"kmg_stream_{budget}.npy")
+        subprocess.run([sys.executable, "-c", code, path], check=True, env=env, timeout=600)
+        outs.append(np.load(path))
+    assert np.array_equal(outs[0], outs[1])
