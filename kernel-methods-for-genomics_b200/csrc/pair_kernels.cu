@@ -281,51 +281,87 @@ mismatch_diag_kernel(const uint32_t* __restrict__ planes, int64_t n, const Misma
 struct WdParams {
     int d;
     int L;
+    uint32_t posmask[4]; // bits 1..L-1 (position 0 is skipped by the reference, kernels.py:78)
     double diag;        // L - 1 + (1 - d) / 3, evaluated on the host like kernels.py:96
     double beta[128];   // beta_k = 2*(d-k+1)/d/(d+1), evaluated on the host like kernels.py:61
 };
 
+// Each thread owns WD_PPT pairs (one row, columns c, c+32, c+64, c+96): the index arithmetic, the row operand, the
+// loop control, the warp vote and the beta_k load are shared (the kernel is issue bound: ncu 87 % of issue slots at
+// one pair per thread, a third of them outside the k loop).  CTA tile 8 rows x 128 columns.
+constexpr int WD_PPT = 4;
+constexpr int WD_TILE_C = TILE_C * WD_PPT;
+
 __global__ void __launch_bounds__(TILE_R * TILE_C)
 wd_kernel(const uint32_t* __restrict__ prow, const uint32_t* __restrict__ pcol, const OutSpec o, const WdParams wp) {
-    __shared__ double tile[TILE_R][TILE_C + 1];
-    const int64_t r0 = (int64_t)blockIdx.y * TILE_R, c0 = (int64_t)blockIdx.x * TILE_C;
-    const int cls = tile_class(o, r0, c0);
-    if (cls == 2) return;
-    const int tr = threadIdx.x >> 5, tc = threadIdx.x & 31;
-    const int64_t r = r0 + tr, c = c0 + tc;
-    const bool live = r < o.rows && c < o.cols;
-    const SeqPlanes x = kmg_load_planes(prow, live ? r : 0);
-    const SeqPlanes y = kmg_load_planes(pcol, live ? c : 0);
-    // positions 1..L-1
-    uint32_t pm[4] = {0u, 0u, 0u, 0u};
-    kmg_range_mask_128(1, wp.L - 1, pm);
-    uint32_t m[4], sh[4];
-#pragma unroll
-    for (int w = 0; w < 4; ++w) {
-        m[w] = ~((x.lo[w] ^ y.lo[w]) | (x.hi[w] ^ y.hi[w])) & pm[w];
-        sh[w] = m[w];
+    __shared__ double tile[TILE_R][WD_TILE_C + 1];
+    const int64_t r0 = (int64_t)blockIdx.y * TILE_R, c0 = (int64_t)blockIdx.x * WD_TILE_C;
+    int cls = 0;
+    if (o.symmetric) {
+        const int64_t rlo = o.row_index0 + r0, rhi = rlo + TILE_R - 1;
+        const int64_t clo = o.col_index0 + c0, chi = clo + WD_TILE_C - 1;
+        if (chi < rlo) return;          // produced by another tile's mirror store
+        cls = clo > rhi ? 1 : 0;        // strictly above the diagonal: mirror
     }
-    double acc = 0.0;
+    const int tr = threadIdx.x >> 5, tc = threadIdx.x & 31;
+    const int64_t r = r0 + tr;
+    const bool row_ok = r < o.rows;
+    const SeqPlanes x = kmg_load_planes(prow, row_ok ? r : 0);
+    uint32_t m[WD_PPT][4], sh[WD_PPT][4];
+#pragma unroll
+    for (int j = 0; j < WD_PPT; ++j) {
+        const int64_t c = c0 + tc + 32 * j;
+        const SeqPlanes y = kmg_load_planes(pcol, c < o.cols ? c : 0);
+#pragma unroll
+        for (int w = 0; w < 4; ++w) {
+            m[j][w] = ~((x.lo[w] ^ y.lo[w]) | (x.hi[w] ^ y.hi[w])) & wp.posmask[w];  // positions 1..L-1
+            sh[j][w] = m[j][w];
+        }
+    }
+    double acc[WD_PPT];
+#pragma unroll
+    for (int j = 0; j < WD_PPT; ++j) acc[j] = 0.0;
 #pragma unroll 1
     for (int k = 1; k <= wp.d; ++k) {
-        if (k > 1) {
-            kmg_shr1_128(sh);
+        uint32_t any = 0u;
 #pragma unroll
-            for (int w = 0; w < 4; ++w) m[w] &= sh[w];
+        for (int j = 0; j < WD_PPT; ++j) {
+            if (k > 1) {
+                kmg_shr1_128(sh[j]);
+#pragma unroll
+                for (int w = 0; w < 4; ++w) m[j][w] &= sh[j][w];
+            }
+            any |= m[j][0] | m[j][1] | m[j][2] | m[j][3];
         }
-        // all 32 pairs of this warp have no run of length k left: the remaining terms add +0.0
-        if (__all_sync(0xffffffffu, (m[0] | m[1] | m[2] | m[3]) == 0u)) break;
-        const int cnt = __popc(m[0]) + __popc(m[1]) + __popc(m[2]) + __popc(m[3]);
-        acc = __dadd_rn(acc, __dmul_rn(wp.beta[k - 1], (double)cnt));
+        // none of the 128 pairs of this warp has a run of length k left: the remaining terms add +0.0
+        if (__all_sync(0xffffffffu, any == 0u)) break;
+        const double bk = wp.beta[k - 1];
+#pragma unroll
+        for (int j = 0; j < WD_PPT; ++j) {
+            // The XU pipe (POPC, I2F) is the busiest one (ncu 65 %): a carry-save adder over three of the four words
+            // trades one POPC for two LOP3, and the exact int -> double conversion is one FP64 add of 2^52.
+            const uint32_t s3 = m[j][0] ^ m[j][1] ^ m[j][2];
+            const uint32_t cy = (m[j][0] & m[j][1]) | (m[j][2] & (m[j][0] ^ m[j][1]));
+            const int cnt = __popc(s3) + 2 * __popc(cy) + __popc(m[j][3]);
+            const double cd = __hiloint2double(0x43300000, cnt) - 4503599627370496.0;
+            acc[j] = __dadd_rn(acc[j], __dmul_rn(bk, cd));
+        }
     }
-    if (o.row_index0 + r == o.col_index0 + c) acc = wp.diag;
-    if (live) reinterpret_cast<double*>(o.out)[r * o.ldo + c] = acc;
+#pragma unroll
+    for (int j = 0; j < WD_PPT; ++j) {
+        const int64_t c = c0 + tc + 32 * j;
+        if (o.row_index0 + r == o.col_index0 + c) acc[j] = wp.diag;
+        if (row_ok && c < o.cols) reinterpret_cast<double*>(o.out)[r * o.ldo + c] = acc[j];
+        if (cls == 1) tile[tr][tc + 32 * j] = acc[j];
+    }
     if (cls == 1) {  // mirror through shared memory so each column receives 8 consecutive doubles
-        tile[tr][tc] = acc;
         __syncthreads();
-        const int mc = threadIdx.x >> 3, mr = threadIdx.x & 7;
-        if (r0 + mr < o.rows && c0 + mc < o.cols)
-            reinterpret_cast<double*>(o.out_t)[(c0 + mc) * o.ldo_t + r0 + mr] = tile[mr][mc];
+#pragma unroll
+        for (int j = 0; j < WD_PPT; ++j) {
+            const int mc = (threadIdx.x >> 3) + 32 * j, mr = threadIdx.x & 7;
+            if (r0 + mr < o.rows && c0 + mc < o.cols)
+                reinterpret_cast<double*>(o.out_t)[(c0 + mc) * o.ldo_t + r0 + mr] = tile[mr][mc];
+        }
     }
 }
 
@@ -546,7 +582,9 @@ int kmg_wd_launch(const PairBlock* b, int d, cudaStream_t stream) {
         wp.beta[k - 1] = k <= d ? (double)(2 * (d - k + 1)) / (double)d / (double)(d + 1) : 0.0;  // kernels.py:61
     wp.beta[127] = 0.0;
     const OutSpec o = make_out(b);
-    dim3 grid((unsigned)((b->cols + TILE_C - 1) / TILE_C), (unsigned)((b->rows + TILE_R - 1) / TILE_R));
+    for (int w = 0; w < 4; ++w) wp.posmask[w] = 0u;
+    if (b->L >= 2) kmg_range_mask_128(1, b->L - 1, wp.posmask);
+    dim3 grid((unsigned)((b->cols + WD_TILE_C - 1) / WD_TILE_C), (unsigned)((b->rows + TILE_R - 1) / TILE_R));
     wd_kernel<<<grid, TILE_R * TILE_C, 0, stream>>>(b->planes_rows, b->planes_cols, o, wp);
     KMG_CUDA_CHECK(cudaGetLastError());
     return KMG_OK;
