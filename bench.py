@@ -298,7 +298,7 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu:
         import oracle_c as oc
         oc.build()
-        rows, cols = cpu_sample_shape(4.0, oc)
+        rows, cols = cpu_sample_shape(8.0, oc)
         v, dtc = run_cpu(rows, cols, 3, 0, oc)
         line["cpu_baseline"] = {"value": v, "unit": "entries/s", "cores": oc.num_threads(), "kind": "port",
                                 "sample": f"{rows} x {cols} entries of the block-row, 3 timed passes of {dtc:.1f} s (oracle/kmg_oracle.c: "

@@ -619,8 +619,18 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const KernelParams& p
         attr_set[dev & 63] = true;
     }
     const int grid = p.ntiles < sms ? p.ntiles : sms;
-    gram_i8_tcgen05_kernel<M_SUB><<<grid, NUM_THREADS, C::SMEM_BYTES, stream>>>(tmA, tmB, p);
-    KMG_CUDA_CHECK(cudaGetLastError());
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = C::SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    // the wave barrier needs every CTA resident: a cooperative launch makes the driver guarantee it (or fail the launch)
+    attr[0].id = cudaLaunchAttributeCooperative;
+    attr[0].val.cooperative = p.wave_counter != nullptr ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    KMG_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gram_i8_tcgen05_kernel<M_SUB>, tmA, tmB, p));
     return KMG_OK;
 }
 
@@ -639,13 +649,16 @@ int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const KernelPara
     cfg.blockDim = dim3(NUM_THREADS);
     cfg.dynamicSmemBytes = Cfg2::SMEM_BYTES;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    // the wave barrier needs every CTA resident: a cooperative launch makes the driver guarantee it (or fail the launch)
+    attr[1].id = cudaLaunchAttributeCooperative;
+    attr[1].val.cooperative = p.wave_counter != nullptr ? 1 : 0;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = 2;
     KMG_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gram_i8_2cta_kernel, tmA, tmB, p));
     return KMG_OK;
 }
