@@ -38,6 +38,13 @@ constexpr int UMMA_K = 32;
 constexpr int NUM_EPI_WARPS = 8;
 constexpr int NUM_THREADS = 128 + 32 * NUM_EPI_WARPS;
 constexpr int TMEM_COLS = 512;
+// Warp roles.  The epilogue warps take the LOW warp ids and the TMA producer / MMA issuer the HIGH ones: the SM
+// sub-partition arbiter favours the highest warp id, and an MMA-issuing thread that loses issue slots to two busy
+// epilogue warps on its sub-partition starves the tensor pipe (measured: a leaner epilogue made the large-D GEMM 3 %
+// slower until the roles were swapped).  Epilogue warp w reads TMEM lanes 32*(w%4) .. +31 (hardware rule).
+constexpr int WARP_TMA = NUM_EPI_WARPS;
+constexpr int WARP_MMA = NUM_EPI_WARPS + 1;
+constexpr int WARP_ALLOC = NUM_EPI_WARPS + 2;
 
 struct KernelParams {
     int64_t rows, cols;
@@ -108,6 +115,52 @@ __device__ __forceinline__ void store_chunk(const KernelParams& p, const uint32_
     const int64_t col = col0 + 2 * l16;  // this lane stores columns col, col+1
     const int ok = (2 * l16 + 1 < ncol) ? 2 : ((2 * l16 < ncol) ? 1 : 0);
     const bool norm = p.sd_rows != nullptr;
+    // Fast path for interior chunks (all but the last tile row / column): no per-element bounds or alignment tests and
+    // one 64-bit pointer increment per pair of rows -- the general path below spends ~20 instructions per element on
+    // index arithmetic and predicates, which is what bounds the write-bound small-D regime (ncu: issue slots spread
+    // over the epilogue, no single stall).
+    // Only in the kernels whose epilogue is on the critical path (INT_CVT == false: small D, or the serial-epilogue
+    // variants): under a long main loop the leaner, burstier store stream measurably slows the MMA pipeline
+    // (25k x 200k block-row: 54.3 ms with the general path, 56.5 ms with this one), and the epilogue is hidden anyway.
+    if (!INT_CVT && nrow == 32 && ncol == 32 && !norm && (p.ldo & 1) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0) {
+        const uint32_t* src = stage + half * 32 + ((l16 & 1) << 1);
+        const int cl = l16 >> 1;
+        if (p.out_dtype == KMG_OUT_S32) {
+            int32_t* dst = reinterpret_cast<int32_t*>(p.out) + (row_base + half) * p.ldo + col;
+            const int64_t step = 2 * p.ldo;
+#pragma unroll 4
+            for (int r2 = 0; r2 < 16; ++r2) {
+                const int rr = 2 * r2 + half;
+                const uint2 iv = *reinterpret_cast<const uint2*>(src + r2 * 64 + ((cl ^ (rr & 7)) << 2));
+                *reinterpret_cast<int2*>(dst) = make_int2((int)iv.x, (int)iv.y);
+                dst += step;
+            }
+        } else {
+            double* dst = reinterpret_cast<double*>(p.out) + (row_base + half) * p.ldo + col;
+            const int64_t step = 2 * p.ldo;
+#pragma unroll 4
+            for (int r2 = 0; r2 < 16; ++r2) {
+                const int rr = 2 * r2 + half;
+                const uint2 iv = *reinterpret_cast<const uint2*>(src + r2 * 64 + ((cl ^ (rr & 7)) << 2));
+                *reinterpret_cast<double2*>(dst) = make_double2(u32_to_f64<INT_CVT>(iv.x), u32_to_f64<INT_CVT>(iv.y));
+                dst += step;
+            }
+        }
+        if (mirror) {
+            const int64_t row_t = row_base + lane;
+            if (p.out_dtype == KMG_OUT_S32) {
+                int32_t* dt = reinterpret_cast<int32_t*>(p.out_t) + col0 * p.ldo_t + row_t;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) { *dt = (int32_t)v[j]; dt += p.ldo_t; }
+            } else {
+                double* dt = reinterpret_cast<double*>(p.out_t) + col0 * p.ldo_t + row_t;
+#pragma unroll
+                for (int j = 0; j < 32; ++j) { *dt = u32_to_f64<INT_CVT>(v[j]); dt += p.ldo_t; }
+            }
+        }
+        __syncwarp();
+        return;
+    }
     if (p.out_dtype == KMG_OUT_S32) {
         int32_t* base = reinterpret_cast<int32_t*>(p.out);
         const bool vec = ((p.ldo & 1) == 0) && ((reinterpret_cast<uintptr_t>(base) & 7) == 0);
@@ -191,11 +244,11 @@ gram_i8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
 
-    if (warp == 0 && lane == 0) {
+    if (warp == WARP_TMA && lane == 0) {
         ptx::prefetch_tensormap(&tmA);
         ptx::prefetch_tensormap(&tmB);
     }
-    if (warp == 1 && lane == 0) {
+    if (warp == WARP_MMA && lane == 0) {
         for (int s = 0; s < C::STAGES; ++s) {
             ptx::mbar_init(&full[s], 1);
             ptx::mbar_init(&empty[s], 1);
@@ -206,7 +259,7 @@ gram_i8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         }
         ptx::fence_barrier_init();
     }
-    if (warp == 2) {
+    if (warp == WARP_ALLOC) {
         ptx::tmem_alloc(tmem_slot, TMEM_COLS);
         ptx::tmem_relinquish();
     }
@@ -215,7 +268,7 @@ gram_i8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     ptx::tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 0) {
+    if (warp == WARP_TMA) {
         // ------------------------------------------------------------ TMA producer
         if (lane == 0) {
             uint32_t stage = 0, phase = 0, wave = 0;
@@ -249,7 +302,7 @@ gram_i8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             }
         }
         __syncwarp();
-    } else if (warp == 1) {
+    } else if (warp == WARP_MMA) {
         // ------------------------------------------------------------ MMA issuer
         if (lane == 0) {
             constexpr uint32_t idesc = ptx::make_idesc_i8(128, BN);
@@ -280,10 +333,10 @@ gram_i8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             }
         }
         __syncwarp();
-    } else if (warp >= 4) {
+    } else if (warp < NUM_EPI_WARPS) {
         // ------------------------------------------------------------ epilogue
         const int quarter = warp & 3;        // TMEM lane quarter this warp may access
-        const int half = (warp - 4) >> 2;    // which 128 of the 256 accumulator columns
+        const int half = warp >> 2;    // which 128 of the 256 accumulator columns
         uint32_t acc = 0, acc_phase = 0;
         for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
             const int4 tile = p.tiles[t];
@@ -302,7 +355,7 @@ gram_i8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                     uint32_t v[32];
                     ptx::tmem_ld_32x32b_x32(taddr, v);
                     ptx::tmem_ld_wait();
-                    store_chunk<false>(p, v, epi_stage + (warp - 4) * C::EPI_STAGE_WORDS, lane, row_base, col0, mirror);
+                    store_chunk<false>(p, v, epi_stage + warp * C::EPI_STAGE_WORDS, lane, row_base, col0, mirror);
                 }
             }
             ptx::tcgen05_fence_before();
@@ -313,7 +366,7 @@ gram_i8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     }
     ptx::tcgen05_fence_before();
     __syncthreads();
-    if (warp == 2) {
+    if (warp == WARP_ALLOC) {
         ptx::tcgen05_fence_after();
         ptx::tmem_dealloc(tmem_base, TMEM_COLS);
     }
@@ -340,6 +393,7 @@ struct Cfg2 {
     static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + NUM_EPI_WARPS * EPI_STAGE_WORDS * 4;
 };
 
+template <bool INT_CVT>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gram_i8_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const KernelParams p) {
     using C = Cfg2;
@@ -359,11 +413,11 @@ gram_i8_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int cluster_id = blockIdx.x >> 1;
     const int num_clusters = gridDim.x >> 1;
 
-    if (warp == 0 && lane == 0) {
+    if (warp == WARP_TMA && lane == 0) {
         ptx::prefetch_tensormap(&tmA);
         ptx::prefetch_tensormap(&tmB);
     }
-    if (warp == 1 && lane == 0) {
+    if (warp == WARP_MMA && lane == 0) {
         for (int s = 0; s < C::STAGES; ++s) {
             ptx::mbar_init(&full[s], 1);    // leader: its own arrive.expect_tx for the bytes of both CTAs
             ptx::mbar_init(&empty[s], 1);   // multicast tcgen05.commit
@@ -374,7 +428,7 @@ gram_i8_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         }
         ptx::fence_barrier_init();
     }
-    if (warp == 2) {
+    if (warp == WARP_ALLOC) {
         ptx::tmem_alloc_2cta(tmem_slot, TMEM_COLS);
         ptx::tmem_relinquish_2cta();
     }
@@ -383,7 +437,7 @@ gram_i8_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     ptx::tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 0) {
+    if (warp == WARP_TMA) {
         // ------------------------------------------------------------ TMA producer (both CTAs)
         if (lane == 0) {
             uint32_t stage = 0, phase = 0, wave = 0;
@@ -413,7 +467,7 @@ gram_i8_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
         }
         __syncwarp();
-    } else if (warp == 1) {
+    } else if (warp == WARP_MMA) {
         // ------------------------------------------------------------ MMA issuer (leader CTA only)
         if (lane == 0 && rank == 0) {
             constexpr uint32_t idesc = ptx::make_idesc_i8(256, BN);
@@ -440,10 +494,10 @@ gram_i8_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             }
         }
         __syncwarp();
-    } else if (warp >= 4) {
+    } else if (warp < NUM_EPI_WARPS) {
         // ------------------------------------------------------------ epilogue (both CTAs, own 128 rows)
         const int quarter = warp & 3;
-        const int half = (warp - 4) >> 2;
+        const int half = warp >> 2;
         uint32_t acc = 0, acc_phase = 0;
         for (int t = cluster_id; t < p.ntiles; t += num_clusters) {
             const int4 tile = p.tiles[t];
@@ -451,6 +505,9 @@ gram_i8_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             ptx::mbar_wait(&tfull[acc], acc_phase);
             ptx::tcgen05_fence_after();
             const int64_t row_base = (int64_t)tile.x * C::BM + (int64_t)rank * 128 + quarter * 32;
+            // (software-pipelining the tcgen05.ld of chunk c+1 under the stores of chunk c was measured: no gain, and the
+            // unrolled copies of the store code blew the kernel up to 250 KB of SASS, which cost 3 % on the large-D shapes)
+            uint32_t* st = epi_stage + warp * C::EPI_STAGE_WORDS;
 #pragma unroll 1
             for (int ch = 0; ch < 4; ++ch) {
                 const int64_t col0 = (int64_t)tile.y * BN + half * 128 + ch * 32;
@@ -459,7 +516,7 @@ gram_i8_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 uint32_t v[32];
                 ptx::tmem_ld_32x32b_x32(taddr, v);
                 ptx::tmem_ld_wait();
-                store_chunk<true>(p, v, epi_stage + (warp - 4) * C::EPI_STAGE_WORDS, lane, row_base, col0, mirror);
+                store_chunk<INT_CVT>(p, v, st, lane, row_base, col0, mirror);
             }
             ptx::tcgen05_fence_before();
             __syncwarp();
@@ -469,7 +526,7 @@ gram_i8_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     ptx::tcgen05_fence_before();
     ptx::cluster_sync_all();
-    if (warp == 2) {
+    if (warp == WARP_ALLOC) {
         ptx::tcgen05_fence_after();
         ptx::tmem_dealloc_2cta(tmem_base, TMEM_COLS);
     }
@@ -634,12 +691,13 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const KernelParams& p
     return KMG_OK;
 }
 
+template <bool INT_CVT>
 int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const KernelParams& p, int sms, cudaStream_t stream) {
     static bool attr_set[64] = {};
     int dev = 0;
     KMG_CUDA_CHECK(cudaGetDevice(&dev));
     if (!attr_set[dev & 63]) {
-        KMG_CUDA_CHECK(cudaFuncSetAttribute(gram_i8_2cta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg2::SMEM_BYTES));
+        KMG_CUDA_CHECK(cudaFuncSetAttribute(gram_i8_2cta_kernel<INT_CVT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg2::SMEM_BYTES));
         attr_set[dev & 63] = true;
     }
     int clusters = sms / 2;
@@ -659,7 +717,7 @@ int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const KernelPara
     attr[1].val.cooperative = p.wave_counter != nullptr ? 1 : 0;
     cfg.attrs = attr;
     cfg.numAttrs = 2;
-    KMG_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gram_i8_2cta_kernel, tmA, tmB, p));
+    KMG_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gram_i8_2cta_kernel<INT_CVT>, tmA, tmB, p));
     return KMG_OK;
 }
 
@@ -722,7 +780,8 @@ int kmg_gram_i8_launch(const GramI8Args* a, cudaStream_t stream) {
     }
     p.hint_a = hint_mode == 1 ? ptx::L2_EVICT_LAST : ptx::L2_EVICT_NORMAL;
     p.hint_b = hint_mode == 2 ? ptx::L2_EVICT_FIRST : ptx::L2_EVICT_NORMAL;
-    if (pair) return launch_pair(tmA, tmB, p, sms, stream);
+    // FP64-pipe instructions stall behind a saturated tensor pipe: integer conversion once the main loop dominates
+    if (pair) return a->Dpad >= 3072 ? launch_pair<true>(tmA, tmB, p, sms, stream) : launch_pair<false>(tmA, tmB, p, sms, stream);
     return m_sub == 1 ? launch<1>(tmA, tmB, p, sms, stream) : launch<2>(tmA, tmB, p, sms, stream);
 }
 
