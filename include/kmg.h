@@ -52,6 +52,12 @@ const char* kmg_last_error(void);
 int kmg_device_count(void);          /* 0 when no usable CUDA device */
 int kmg_set_device(int device);
 int kmg_release(void);               /* frees cached device buffers of the current device */
+/* plain device buffers for callers that keep Grams resident between calls (kmg/resident.py: NLCK's 50 iterations
+ * reuse the fit sub-blocks instead of re-uploading them); synchronous copies on the default stream */
+int kmg_dev_malloc(int64_t bytes, void** ptr);
+int kmg_dev_free(void* ptr);
+int kmg_dev_upload(void* d_dst, const void* h_src, int64_t bytes);
+int kmg_dev_download(void* h_dst, const void* d_src, int64_t bytes);
 
 /* ---- host-buffer entry points (the reference-facing boundary) ------------------------------ */
 /* cols == NULL: symmetric Gram of `rows` (n x n, upper triangle computed and mirrored, as the

@@ -5,6 +5,7 @@ Same class, constructor and method names as the reference (NLCKernels.py:12-100)
   * normalize_kernels: normalize_K of every kernel, in place (NLCKernels.py:43-48),
   * the K-line of svm_step, (sum_m u_m K_m) ** degree on the fit sub-blocks (NLCKernels.py:52),
   * grad: -degree * alpha' ((sum u K)^(degree-1) o K_m) alpha for every m (NLCKernels.py:61-66),
+    -- both on fit sub-blocks uploaded once and kept resident in HBM (kmg/resident.py) for all iterations,
   * get_K: (sum_m u*_m K_m) ** degree followed by normalize_K over the full kernels (NLCKernels.py:97-99).
 What stays as in the reference: the cvxopt QP of svm_step (NLCKernels.py:53-59) and the projected-gradient loop
 (NLCKernels.py:68-92) -- solver code, outside the hot path.  cvxopt is imported lazily, so
@@ -14,6 +15,7 @@ import numpy as np
 
 from kernels import normalize_K
 from kmg import host as _host
+from kmg import resident as _res
 
 
 class NLCK():
@@ -35,6 +37,14 @@ class NLCK():
         self.lbda = 1 / (2 * self.C * self.n)
         self.eps = eps
         self.degree = degree
+        self._fit_dev = None  # fit sub-blocks resident in HBM for the whole projected-gradient loop
+
+    def _resident(self):
+        """Upload the p fit sub-blocks once; svm_step and grad then re-use them every iteration."""
+        if self._fit_dev is None:
+            grams = [_res.DeviceGram.from_host(K) for K in self.kernels_fit]
+            self._fit_dev = (grams, _res.QuadForms(grams), _res.DeviceGram(self.kernels_fit[0].shape[0]))
+        return self._fit_dev
 
     def normalize_kernels(self, kernels):
         """NLCKernels.py:43-48 (normalize_K mutates its argument and returns it)."""
@@ -49,7 +59,8 @@ class NLCK():
         from cvxopt import matrix, spmatrix, solvers
         solvers.options['show_progress'] = False
         r, o, z = np.arange(self.n), np.ones(self.n), np.zeros(self.n)
-        K = _host.combine(self.kernels_fit, u, degree=self.degree)
+        grams, _, out = self._resident()
+        K = _res.combine(grams, u, degree=self.degree, out=out).to_host()
         P = matrix(K.astype(float), tc='d')
         q = matrix(-self.y, tc='d')
         G = spmatrix(np.r_[self.y, -self.y], np.r_[r, r + self.n], np.r_[r, r], tc='d')
@@ -59,7 +70,7 @@ class NLCK():
 
     def grad(self, u, alpha):
         """NLCKernels.py:61-66."""
-        return _host.nlck_grad(self.kernels_fit, u, alpha, self.degree)
+        return self._resident()[1].grad(u, alpha, self.degree)
 
     def normalize(self, u, u0, fnorm):
         """NLCKernels.py:68-72."""

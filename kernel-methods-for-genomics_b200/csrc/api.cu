@@ -372,6 +372,42 @@ int kmg_set_device(int device) {
     return KMG_OK;
 }
 
+// ---- plain device buffers for callers that keep Grams resident between calls (kmg/resident.py) ----
+int kmg_dev_malloc(int64_t bytes, void** ptr) {
+    int rc = require_device();
+    if (rc) return rc;
+    KMG_REQUIRE(bytes >= 0 && ptr != nullptr, KMG_ERR_ARG, "dev_malloc: bad arguments");
+    *ptr = nullptr;
+    if (bytes == 0) return KMG_OK;
+    cudaError_t e = cudaMalloc(ptr, (size_t)bytes);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        { std::lock_guard<std::mutex> lk(g_cache.mu); g_cache.flush(); }
+        e = cudaMalloc(ptr, (size_t)bytes);
+    }
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        kmg_set_error("cudaMalloc(%lld bytes) failed: %s", (long long)bytes, cudaGetErrorString(e));
+        return KMG_ERR_NOMEM;
+    }
+    return KMG_OK;
+}
+
+int kmg_dev_free(void* ptr) {
+    if (ptr) KMG_CUDA_CHECK(cudaFree(ptr));
+    return KMG_OK;
+}
+
+int kmg_dev_upload(void* d_dst, const void* h_src, int64_t bytes) {
+    if (bytes > 0) KMG_CUDA_CHECK(cudaMemcpy(d_dst, h_src, (size_t)bytes, cudaMemcpyHostToDevice));
+    return KMG_OK;
+}
+
+int kmg_dev_download(void* h_dst, const void* d_src, int64_t bytes) {
+    if (bytes > 0) KMG_CUDA_CHECK(cudaMemcpy(h_dst, d_src, (size_t)bytes, cudaMemcpyDeviceToHost));
+    return KMG_OK;
+}
+
 int kmg_release(void) {
     std::lock_guard<std::mutex> lk(g_cache.mu);
     int dev = 0;

@@ -34,6 +34,10 @@ PROTOTYPES = {
     "kmg_device_count": (_i32, []),
     "kmg_set_device": (_i32, [_i32]),
     "kmg_release": (_i32, []),
+    "kmg_dev_malloc": (_i32, [_i64, _vp]),
+    "kmg_dev_free": (_i32, [_vp]),
+    "kmg_dev_upload": (_i32, [_vp, _vp, _i64]),
+    "kmg_dev_download": (_i32, [_vp, _vp, _i64]),
     "kmg_spectrum_host": (_i32, [_vp, _i64, _vp, _i64, _i32, _i32, _vp, _i32, _vp, _i64]),
     "kmg_mismatch_host": (_i32, [_vp, _i64, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _i64]),
     "kmg_spectrum_phi_host": (_i32, [_vp, _i64, _i32, _i32, _vp, _i32, _vp, _i64]),

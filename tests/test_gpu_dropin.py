@@ -139,6 +139,40 @@ def test_alignf_nlck_algebra(golden):
             assert np.array_equal(Km, golden[f"nlck_Km_deg{deg}"]), deg     # deg 1, 2: bit-exact (x*x == np.square)
 
 
+def test_resident_grams(golden):
+    """kmg/resident.py: Grams uploaded once and re-used -- same bits as the per-call host entry points."""
+    from kmg import host, resident
+    Ks = [golden[f"alignf_K{i}"] for i in range(3)]
+    idx = golden["alignf_fit_rows"]
+    dev = [resident.DeviceGram.from_host(k) for k in Ks]
+    assert np.array_equal(dev[1].to_host(), Ks[1])
+    assert dev[0].normalize_() is False
+    Kn = [k.copy() for k in Ks]
+    host.normalize_inplace(Kn[0])
+    assert np.array_equal(dev[0].to_host(), Kn[0]) and np.array_equal(Kn[0], golden["nlck_K0_normalized"])
+    assert dev[0].normalize_() is True                                   # K[0,0] == 1 early-out (kernels.py:403)
+    for g in dev[1:]:
+        g.normalize_()
+    for k in Kn[1:]:
+        host.normalize_inplace(k)
+    fit_dev = [g.gather(idx) for g in dev]
+    fit = [np.ascontiguousarray(k[idx][:, idx]) for k in Kn]
+    for a, b in zip(fit_dev, fit):
+        assert np.array_equal(a.to_host(), b)
+    u, alpha = golden["nlck_u"], golden["nlck_alpha"]
+    q = resident.QuadForms(fit_dev)
+    for deg in (1, 2, 3):
+        for _ in range(2):                                               # second call re-uses every buffer
+            g = q.grad(u, alpha, deg)
+            assert np.array_equal(g, host.nlck_grad(fit, u, alpha, deg)), deg
+        ref = golden[f"nlck_grad_deg{deg}"]
+        assert np.all(np.abs(g - ref) <= 1e-12 * np.abs(ref).max()), deg
+        assert np.array_equal(resident.combine(fit_dev, u, deg).to_host(), host.combine(fit, u, deg)), deg
+    for g in dev + fit_dev:
+        g.free()
+        g.free()                                                         # idempotent
+
+
 def test_wds_dropin(km, golden, X0):
     assert np.array_equal(km.select_method(X0.iloc[:12], "WDS_d3_s2"), golden["wds_d3_s2_n12"])
     assert np.array_equal(km.get_WDShifts_K(X0.iloc[:10], 5, 1), golden["wds_d5_s1_n10"])
