@@ -51,13 +51,18 @@ int kmg_version(void);
 const char* kmg_last_error(void);
 int kmg_device_count(void);          /* 0 when no usable CUDA device */
 int kmg_set_device(int device);
-int kmg_release(void);               /* frees cached device buffers of the current device */
+int kmg_release(void);               /* frees cached device buffers of the current device and cached host blocks */
 /* plain device buffers for callers that keep Grams resident between calls (kmg/resident.py: NLCK's 50 iterations
  * reuse the fit sub-blocks instead of re-uploading them); synchronous copies on the default stream */
 int kmg_dev_malloc(int64_t bytes, void** ptr);
 int kmg_dev_free(void* ptr);
 int kmg_dev_upload(void* d_dst, const void* h_src, int64_t bytes);
 int kmg_dev_download(void* h_dst, const void* d_src, int64_t bytes);
+/* recycled host memory for result arrays (every reference builder allocates its result, e.g. kernels.py:37 np.zeros):
+ * 2 MB aligned, huge-page advised, pageable; kmg_host_free returns the block to a bounded cache
+ * (KMG_HOST_POOL_BYTES, default 8 GiB; kmg_release empties it) so later results land in memory that is already mapped */
+int kmg_host_alloc(int64_t bytes, void** ptr);
+int kmg_host_free(void* ptr);
 
 /* ---- host-buffer entry points (the reference-facing boundary) ------------------------------ */
 /* cols == NULL: symmetric Gram of `rows` (n x n, upper triangle computed and mirrored, as the

@@ -7,6 +7,9 @@
 #include <stdio.h>
 #include <string.h>
 #include <sys/mman.h>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 
 #include <algorithm>
 #include <chrono>
@@ -201,13 +204,31 @@ int ring_init() {
     return KMG_OK;
 }
 
-// src: device, `rows` x `cols` doubles, contiguous.  dst: host, row stride ldk.
-int d2h_rows(double* dst, int64_t ldk, const double* src, int64_t cols, int64_t rows, cudaStream_t s) {
+// int32 -> double widening of one staged row into the caller's memory (exact: every s32 is a double).  Streaming
+// stores: the destination is written once and not read back here, so skip the read-for-ownership.
+void widen_s32_row(double* __restrict__ dst, const int32_t* __restrict__ src, int64_t n) {
+    int64_t j = 0;
+#if defined(__SSE2__)
+    while (j < n && (reinterpret_cast<uintptr_t>(dst + j) & 15)) { dst[j] = (double)src[j]; ++j; }
+    for (; j + 4 <= n; j += 4) {
+        const __m128i v = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + j));
+        _mm_stream_pd(dst + j, _mm_cvtepi32_pd(v));
+        _mm_stream_pd(dst + j + 2, _mm_cvtepi32_pd(_mm_shuffle_epi32(v, 0xEE)));
+    }
+#endif
+    for (; j < n; ++j) dst[j] = (double)src[j];
+}
+
+// src: device, `rows` x `cols` contiguous, doubles or (src_s32) int32 counts that the copy threads widen to double on
+// the way into the caller's buffer -- an unnormalised spectrum Gram is integer valued, so shipping the tensor cores'
+// own s32 accumulators halves the PCIe bytes per entry.  dst: host doubles, row stride ldk.
+int d2h_rows(double* dst, int64_t ldk, const void* src_v, bool src_s32, int64_t cols, int64_t rows, cudaStream_t s) {
     if (rows <= 0 || cols <= 0) return KMG_OK;
     std::lock_guard<std::mutex> lk(g_ring.mu);
     int rc = ring_init();
     if (rc) return rc;
-    const size_t row_bytes = (size_t)cols * 8;
+    const char* src = static_cast<const char*>(src_v);
+    const size_t row_bytes = (size_t)cols * (src_s32 ? 4 : 8);
     {
         // Freshly allocated numpy memory is first touched by the copy threads below; with transparent huge pages the
         // kernel zero-fills 2 MB at a time instead of taking a fault per 4 KB page.  Advisory: errors are ignored.
@@ -215,7 +236,8 @@ int d2h_rows(double* dst, int64_t ldk, const double* src, int64_t cols, int64_t 
         const uintptr_t hi = (reinterpret_cast<uintptr_t>(dst + (rows - 1) * ldk + cols)) & ~uintptr_t(0x1FFFFF);
         if (hi > lo) madvise(reinterpret_cast<void*>(lo), hi - lo, MADV_HUGEPAGE);
     }
-    if (row_bytes > D2H_SLOT_BYTES) {  // absurdly wide rows: let the driver stage it
+    if (row_bytes > D2H_SLOT_BYTES) {  // absurdly wide rows (callers never ask for s32 here): let the driver stage it
+        KMG_REQUIRE(!src_s32, KMG_ERR_UNSUPPORTED, "rows wider than a staging slot");
         KMG_CUDA_CHECK(cudaMemcpy2DAsync(dst, (size_t)ldk * 8, src, row_bytes, row_bytes, (size_t)rows, cudaMemcpyDeviceToHost, s));
         KMG_CUDA_CHECK(cudaStreamSynchronize(s));
         return KMG_OK;
@@ -228,14 +250,20 @@ int d2h_rows(double* dst, int64_t ldk, const double* src, int64_t cols, int64_t 
         const int64_t nr = std::min<int64_t>(chunk_rows, rows - r);
         if (fut[slot].valid() && fut[slot].get() != 0) err = KMG_ERR_CUDA;
         if (err) break;
-        KMG_CUDA_CHECK(cudaMemcpyAsync(g_ring.buf[slot], src + r * cols, (size_t)nr * row_bytes, cudaMemcpyDeviceToHost, s));
+        KMG_CUDA_CHECK(cudaMemcpyAsync(g_ring.buf[slot], src + (size_t)r * row_bytes, (size_t)nr * row_bytes, cudaMemcpyDeviceToHost, s));
         KMG_CUDA_CHECK(cudaEventRecord(g_ring.ev[slot], s));
         const char* stage = reinterpret_cast<const char*>(g_ring.buf[slot]);
         cudaEvent_t ev = g_ring.ev[slot];
         double* d0 = dst + r * ldk;
         fut[slot] = std::async(std::launch::async, [=]() -> int {
             if (cudaEventSynchronize(ev) != cudaSuccess) return 1;
-            if (ldk == cols) {
+            if (src_s32) {
+                for (int64_t i = 0; i < nr; ++i)
+                    widen_s32_row(d0 + i * ldk, reinterpret_cast<const int32_t*>(stage + (size_t)i * row_bytes), cols);
+#if defined(__SSE2__)
+                _mm_sfence();
+#endif
+            } else if (ldk == cols) {
                 memcpy(d0, stage, (size_t)nr * row_bytes);
             } else {
                 for (int64_t i = 0; i < nr; ++i) memcpy(d0 + i * ldk, stage + (size_t)i * row_bytes, row_bytes);
@@ -249,12 +277,41 @@ int d2h_rows(double* dst, int64_t ldk, const double* src, int64_t cols, int64_t 
     return KMG_OK;
 }
 
-typedef int (*BlockFn)(void* ctx, int64_t r0, int64_t rows, double* d_out, int64_t ldo, int symmetric, cudaStream_t s);
+// ------------------------------------------------------------------------------------------
+// Recycled host memory for results.  A fresh numpy array of a few GB is mmap'ed untouched, so every byte the copy
+// threads write first takes a page fault + kernel zero-fill (measured: ~30 GB/s aggregate over 16 threads, below the
+// PCIe rate), and free() munmaps it again.  Blocks handed out here are 2 MB aligned, huge-page advised, and go back to
+// a bounded cache on release instead of to the kernel, so the second and later results of a job are written into
+// memory that is already mapped.  Pageable memory: nothing is pinned, the cold cost equals plain malloc's.
+// ------------------------------------------------------------------------------------------
+struct HostPool {
+    std::mutex mu;
+    std::map<void*, size_t> live;
+    std::multimap<size_t, void*> cached;
+    size_t cached_bytes = 0;
+    size_t cap() const {
+        if (const char* v = getenv("KMG_HOST_POOL_BYTES")) return (size_t)atof(v);
+        return (size_t)8 << 30;
+    }
+    void trim(size_t keep) {
+        while (cached_bytes > keep && !cached.empty()) {
+            auto it = std::prev(cached.end());
+            munmap(it->second, it->first);
+            cached_bytes -= it->first;
+            cached.erase(it);
+        }
+    }
+};
+HostPool g_hostpool;
+
+typedef int (*BlockFn)(void* ctx, int64_t r0, int64_t rows, void* d_out, int64_t ldo, int symmetric, cudaStream_t s);
 
 // Build an nr x nc Gram block-row by block-row on the device and copy it to host memory.
 // If the whole (square, symmetric) matrix fits it is built in one symmetric launch.
-int build_to_host(int64_t nr, int64_t nc, bool symmetric, BlockFn fn, void* ctx, double* K, int64_t ldk) {
+// out_s32: `fn` writes int32 counts (d2h_rows widens them on the host side of the link).
+int build_to_host(int64_t nr, int64_t nc, bool symmetric, BlockFn fn, void* ctx, double* K, int64_t ldk, bool out_s32 = false) {
     if (nr == 0 || nc == 0) return KMG_OK;
+    const size_t esz = out_s32 ? sizeof(int32_t) : sizeof(double);
     cudaStream_t s0, s1;
     int rc = get_streams(&s0, &s1);
     if (rc) return rc;
@@ -262,11 +319,11 @@ int build_to_host(int64_t nr, int64_t nc, bool symmetric, BlockFn fn, void* ctx,
     if ((rc = pick_block_rows(nr, nc, &br))) return rc;
     if (br >= nr) {
         DevBuf out;
-        if ((rc = out.alloc((size_t)nr * nc * sizeof(double)))) return rc;
+        if ((rc = out.alloc((size_t)nr * nc * esz))) return rc;
         kmg_trace("build_to_host: output allocated");
-        if ((rc = fn(ctx, 0, nr, out.as<double>(), nc, symmetric ? 1 : 0, s0))) return rc;
+        if ((rc = fn(ctx, 0, nr, out.p, nc, symmetric ? 1 : 0, s0))) return rc;
         if (getenv("KMG_TRACE")) { cudaStreamSynchronize(s0); kmg_trace("build_to_host: kernel done"); }
-        rc = d2h_rows(K, ldk, out.as<double>(), nc, nr, s0);
+        rc = d2h_rows(K, ldk, out.p, out_s32, nc, nr, s0);
         kmg_trace("build_to_host: copied to host");
         return rc;
     }
@@ -274,16 +331,16 @@ int build_to_host(int64_t nr, int64_t nc, bool symmetric, BlockFn fn, void* ctx,
     DevBuf buf[2];
     cudaStream_t st[2] = {s0, s1};
     for (int i = 0; i < 2; ++i)
-        if ((rc = buf[i].alloc((size_t)br * nc * sizeof(double)))) return rc;
+        if ((rc = buf[i].alloc((size_t)br * nc * esz))) return rc;
     const int64_t nblocks = (nr + br - 1) / br;
-    if ((rc = fn(ctx, 0, std::min<int64_t>(br, nr), buf[0].as<double>(), nc, 0, st[0]))) return rc;
+    if ((rc = fn(ctx, 0, std::min<int64_t>(br, nr), buf[0].p, nc, 0, st[0]))) return rc;
     for (int64_t b = 0; b < nblocks; ++b) {
         const int64_t r0 = b * br, rows = std::min<int64_t>(br, nr - r0);
         if (b + 1 < nblocks) {
             const int64_t r1 = (b + 1) * br;
-            if ((rc = fn(ctx, r1, std::min<int64_t>(br, nr - r1), buf[(b + 1) & 1].as<double>(), nc, 0, st[(b + 1) & 1]))) return rc;
+            if ((rc = fn(ctx, r1, std::min<int64_t>(br, nr - r1), buf[(b + 1) & 1].p, nc, 0, st[(b + 1) & 1]))) return rc;
         }
-        if ((rc = d2h_rows(K + r0 * ldk, ldk, buf[b & 1].as<double>(), nc, rows, st[b & 1]))) return rc;
+        if ((rc = d2h_rows(K + r0 * ldk, ldk, buf[b & 1].p, out_s32, nc, rows, st[b & 1]))) return rc;
     }
     return KMG_OK;
 }
@@ -318,15 +375,16 @@ int upload_pair(const uint8_t* rows, int64_t nr, const uint8_t* cols, int64_t nc
 struct SpectrumCtx {
     const int8_t* phi_rows; const int8_t* phi_cols; int64_t nc; int64_t width;
     const double* sd_rows; const double* sd_cols;
+    int out_dtype;
 };
-int spectrum_block(void* c, int64_t r0, int64_t rows, double* out, int64_t ldo, int symmetric, cudaStream_t s) {
+int spectrum_block(void* c, int64_t r0, int64_t rows, void* out, int64_t ldo, int symmetric, cudaStream_t s) {
     SpectrumCtx* x = (SpectrumCtx*)c;
     GramI8Args a;
     memset(&a, 0, sizeof(a));
     a.phi_rows = x->phi_rows + r0 * x->width; a.phi_cols = x->phi_cols;
     a.rows = rows; a.cols = x->nc; a.Dpad = x->width; a.ld_phi = x->width;
     a.row_index0 = symmetric ? 0 : r0; a.col_index0 = 0;
-    a.out = out; a.ldo = ldo; a.out_dtype = KMG_OUT_F64; a.symmetric = symmetric; a.out_t = out; a.ldo_t = ldo;
+    a.out = out; a.ldo = ldo; a.out_dtype = x->out_dtype; a.symmetric = symmetric; a.out_t = out; a.ldo_t = ldo;
     a.sd_rows = x->sd_rows ? x->sd_rows + r0 : nullptr; a.sd_cols = x->sd_cols;
     return kmg_gram_i8_launch(&a, s);
 }
@@ -334,7 +392,7 @@ int spectrum_block(void* c, int64_t r0, int64_t rows, double* out, int64_t ldo, 
 struct PairCtx {
     const SeqPair* sp; int L; int kind; int k, m, d, smith; double e, dd, beta; const double* sd; bool index_diag;
 };
-int pair_block(void* c, int64_t r0, int64_t rows, double* out, int64_t ldo, int symmetric, cudaStream_t s) {
+int pair_block(void* c, int64_t r0, int64_t rows, void* out, int64_t ldo, int symmetric, cudaStream_t s) {
     PairCtx* x = (PairCtx*)c;
     PairBlock b;
     memset(&b, 0, sizeof(b));
@@ -408,7 +466,64 @@ int kmg_dev_download(void* h_dst, const void* d_src, int64_t bytes) {
     return KMG_OK;
 }
 
+// ---- recycled host memory for result arrays (kmg/host.py wraps a block as the numpy array it returns) ----
+int kmg_host_alloc(int64_t bytes, void** ptr) {
+    KMG_REQUIRE(bytes >= 0 && ptr != nullptr, KMG_ERR_ARG, "host_alloc: bad arguments");
+    *ptr = nullptr;
+    if (bytes == 0) return KMG_OK;
+    const size_t need = ((size_t)bytes + 0x1FFFFF) & ~(size_t)0x1FFFFF;
+    std::lock_guard<std::mutex> lk(g_hostpool.mu);
+    auto it = g_hostpool.cached.lower_bound(need);
+    if (it != g_hostpool.cached.end() && it->first <= need + need / 4) {
+        *ptr = it->second;
+        g_hostpool.live[it->second] = it->first;
+        g_hostpool.cached_bytes -= it->first;
+        g_hostpool.cached.erase(it);
+        return KMG_OK;
+    }
+    // over-map by 2 MB and trim so that the block is huge-page aligned
+    const size_t span = need + 0x200000;
+    void* raw = mmap(nullptr, span, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+    if (raw == MAP_FAILED) {
+        g_hostpool.trim(0);
+        raw = mmap(nullptr, span, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+    }
+    KMG_REQUIRE(raw != MAP_FAILED, KMG_ERR_NOMEM, "host_alloc: mmap of %lld bytes failed", (long long)bytes);
+    const uintptr_t a = (reinterpret_cast<uintptr_t>(raw) + 0x1FFFFF) & ~uintptr_t(0x1FFFFF);
+    if (a > reinterpret_cast<uintptr_t>(raw)) munmap(raw, a - reinterpret_cast<uintptr_t>(raw));
+    const uintptr_t end = reinterpret_cast<uintptr_t>(raw) + span;
+    if (end > a + need) munmap(reinterpret_cast<void*>(a + need), end - (a + need));
+    madvise(reinterpret_cast<void*>(a), need, MADV_HUGEPAGE);  // advisory
+    *ptr = reinterpret_cast<void*>(a);
+    g_hostpool.live[*ptr] = need;
+    return KMG_OK;
+}
+
+int kmg_host_free(void* ptr) {
+    if (!ptr) return KMG_OK;
+    std::lock_guard<std::mutex> lk(g_hostpool.mu);
+    auto it = g_hostpool.live.find(ptr);
+    KMG_REQUIRE(it != g_hostpool.live.end(), KMG_ERR_ARG, "host_free: pointer was not returned by kmg_host_alloc");
+    const size_t sz = it->second;
+    g_hostpool.live.erase(it);
+    const size_t cap = g_hostpool.cap();
+    if (sz > cap) { munmap(ptr, sz); return KMG_OK; }
+    g_hostpool.cached.emplace(sz, ptr);
+    g_hostpool.cached_bytes += sz;
+    if (g_hostpool.cached_bytes > cap) {  // evict the other blocks, largest first, keeping the one just returned
+        for (auto c = g_hostpool.cached.end(); g_hostpool.cached_bytes > cap && c != g_hostpool.cached.begin();) {
+            --c;
+            if (c->second == ptr) continue;
+            munmap(c->second, c->first);
+            g_hostpool.cached_bytes -= c->first;
+            c = g_hostpool.cached.erase(c);
+        }
+    }
+    return KMG_OK;
+}
+
 int kmg_release(void) {
+    { std::lock_guard<std::mutex> lk(g_hostpool.mu); g_hostpool.trim(0); }
     std::lock_guard<std::mutex> lk(g_cache.mu);
     int dev = 0;
     cudaGetDevice(&dev);
@@ -465,8 +580,10 @@ int kmg_spectrum_host(const uint8_t* rows, int64_t nr, const uint8_t* cols, int6
     }
     KMG_CUDA_CHECK(cudaStreamSynchronize(s));
     kmg_trace("spectrum_host: Phi built");
-    SpectrumCtx ctx{phi_r.as<int8_t>(), pc, sp.nc, width, nullptr, nullptr};
-    return build_to_host(sp.nr, sp.nc, sp.symmetric, spectrum_block, &ctx, K, ldk);
+    // unnormalised counts: ship the s32 accumulators, widen to double on the host side of PCIe
+    const bool s32 = (size_t)sp.nc * 4 <= D2H_SLOT_BYTES && !getenv("KMG_D2H_F64");
+    SpectrumCtx ctx{phi_r.as<int8_t>(), pc, sp.nc, width, nullptr, nullptr, s32 ? KMG_OUT_S32 : KMG_OUT_F64};
+    return build_to_host(sp.nr, sp.nc, sp.symmetric, spectrum_block, &ctx, K, ldk, s32);
 }
 
 int kmg_mismatch_host(const uint8_t* rows, int64_t nr, const uint8_t* cols, int64_t nc, int L, int seq_format,
@@ -505,7 +622,7 @@ int kmg_mismatch_host(const uint8_t* rows, int64_t nr, const uint8_t* cols, int6
             if (sd0 != 1.0) sdp = sd.as<double>();  // normalize_K early-out, kernels.py:404
         }
         KMG_CUDA_CHECK(cudaStreamSynchronize(s));
-        SpectrumCtx ctx{phi_r.as<int8_t>(), pc, sp.nc, width, sdp, sdp};
+        SpectrumCtx ctx{phi_r.as<int8_t>(), pc, sp.nc, width, sdp, sdp, KMG_OUT_F64};
         return build_to_host(sp.nr, sp.nc, sp.symmetric, spectrum_block, &ctx, K, ldk);
     }
     DevBuf sd;

@@ -51,11 +51,40 @@ def _ptr(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
 
+class _HostBlock:
+    """A block of libkmg's recycled host memory (kmg_host_alloc) exposed through the array interface; the numpy array
+    built on it keeps it alive as its `.base`, and the block returns to the library's cache when that array dies."""
+    __slots__ = ("ptr", "__array_interface__")
+
+    def __init__(self, shape):
+        p = C.c_void_p()
+        check(_cabi.lib().kmg_host_alloc(int(np.prod(shape)) * 8, C.byref(p)))
+        self.ptr = p
+        self.__array_interface__ = {"shape": tuple(shape), "typestr": "<f8", "data": (p.value, False), "version": 3}
+
+    def __del__(self):
+        try:
+            _cabi.lib().kmg_host_free(self.ptr)
+        except Exception:  # noqa: BLE001 - interpreter shutdown
+            pass
+
+
+_POOL_MIN_BYTES = 1 << 22
+
+
+def _result(shape):
+    """The float64 array a builder returns (the reference's np.zeros((n, n)), kernels.py:37).  Every entry point
+    writes all of it.  Large results come from the library's recycled host blocks: not zeroed, already mapped."""
+    if int(np.prod(shape)) * 8 < _POOL_MIN_BYTES:
+        return np.zeros(shape, np.float64)
+    return np.asarray(_HostBlock(shape))
+
+
 def spectrum_gram(rows, ks, cols=None):
     """Sum over `ks` of the k-spectrum Grams (one k: get_spectrum_K, kernels.py:28-47). Unnormalised."""
     ks = np.ascontiguousarray(np.atleast_1d(ks), np.int32)
     rbuf, cbuf, fmt, nr, nc = _pair(rows, cols)
-    K = np.zeros((nr, nc), np.float64)
+    K = _result((nr, nc))
     L = rbuf.shape[1] if nr else 1
     check(_cabi.lib().kmg_spectrum_host(_ptr(rbuf), nr, _ptr(cbuf), 0 if cbuf is None else nc, L, fmt,
                                         _ptr(ks), ks.size, _ptr(K), max(nc, 1)))
@@ -67,7 +96,7 @@ def mismatch_gram(rows, k, m, cols=None, normalize=True, algo=0):
     algo: 0 auto (dense feature map + tensor-core GEMM for k <= 8, pairwise bit-vector kernel above),
     1 pairwise, 2 dense."""
     rbuf, cbuf, fmt, nr, nc = _pair(rows, cols)
-    K = np.zeros((nr, nc), np.float64)
+    K = _result((nr, nc))
     L = rbuf.shape[1] if nr else 1
     check(_cabi.lib().kmg_mismatch_host(_ptr(rbuf), nr, _ptr(cbuf), 0 if cbuf is None else nc, L, fmt,
                                         int(k), int(m), 1 if normalize else 0, int(algo), _ptr(K), max(nc, 1)))
@@ -100,7 +129,7 @@ def mismatch_phi(seqs, k, m):
 def wd_gram(rows, d, cols=None):
     """Weighted-degree Gram (get_WD_K, kernels.py:84-101)."""
     rbuf, cbuf, fmt, nr, nc = _pair(rows, cols)
-    K = np.zeros((nr, nc), np.float64)
+    K = _result((nr, nc))
     L = rbuf.shape[1] if nr else 1
     check(_cabi.lib().kmg_wd_host(_ptr(rbuf), nr, _ptr(cbuf), 0 if cbuf is None else nc, L, fmt, int(d), _ptr(K), max(nc, 1)))
     return K
@@ -109,7 +138,7 @@ def wd_gram(rows, d, cols=None):
 def wds_gram(rows, d, S, cols=None):
     """Weighted-degree-with-shifts Gram (get_WDShifts_K, kernels.py:138-155)."""
     rbuf, cbuf, fmt, nr, nc = _pair(rows, cols)
-    K = np.zeros((nr, nc), np.float64)
+    K = _result((nr, nc))
     L = rbuf.shape[1] if nr else 1
     check(_cabi.lib().kmg_wds_host(_ptr(rbuf), nr, _ptr(cbuf), 0 if cbuf is None else nc, L, fmt, int(d), int(S), _ptr(K), max(nc, 1)))
     return K
@@ -118,7 +147,7 @@ def wds_gram(rows, d, S, cols=None):
 def la_gram(rows, e, d, beta, smith=0, cols=None):
     """Local-alignment Gram with the INTENDED recursion (kernels.py:226-291 as meant)."""
     rbuf, cbuf, fmt, nr, nc = _pair(rows, cols)
-    K = np.zeros((nr, nc), np.float64)
+    K = _result((nr, nc))
     L = rbuf.shape[1] if nr else 1
     check(_cabi.lib().kmg_la_host(_ptr(rbuf), nr, _ptr(cbuf), 0 if cbuf is None else nc, L, fmt,
                                   float(e), float(d), float(beta), int(smith), _ptr(K), max(nc, 1)))
@@ -150,7 +179,7 @@ def center(K):
     """center_K (kernels.py:387-395); returns a new array."""
     K = np.ascontiguousarray(_square_f64(K, "center_K"))
     n = K.shape[0]
-    out = np.empty_like(K)
+    out = _result(K.shape)
     check(_cabi.lib().kmg_center_host(_ptr(K), n, max(n, 1), _ptr(out), max(n, 1)))
     return out
 
@@ -171,7 +200,7 @@ def combine(kernels, u, degree=1, normalize=False):
     u = np.ascontiguousarray(u, np.float64)
     if u.size != len(mats):
         raise ValueError("combine: one weight per kernel")
-    out = np.empty((n, n), np.float64)
+    out = _result((n, n))
     check(_cabi.lib().kmg_combine_host(arr, len(mats), n, _ptr(u), int(degree), 1 if normalize else 0, _ptr(out)))
     return out
 

@@ -83,3 +83,30 @@ def test_argument_errors_are_value_errors():
     assert buf.shape == (2, 4) and fmt == 1
     buf, fmt = host.as_seq_buffer(np.zeros((2, 5), np.uint8))
     assert fmt == 0
+
+
+def test_result_blocks_are_recycled():
+    """kmg_host_alloc / kmg_host_free (the memory behind every large result array): 2 MB aligned, kept alive by numpy
+    views, handed out again after the last view dies, unmapped by kmg_release, foreign pointers rejected."""
+    import gc
+    from kmg import _cabi, host
+    a = host._result((1024, 1024))
+    assert a.dtype == np.float64 and a.flags["C_CONTIGUOUS"] and a.flags["WRITEABLE"] and a.ctypes.data % (1 << 21) == 0
+    a[:] = 3.0
+    addr = a.ctypes.data
+    view = a[5:7]
+    del a
+    gc.collect()
+    b = host._result((1024, 1024))                  # the first block is still referenced by `view`
+    assert b.ctypes.data != addr and view.sum() == 2 * 1024 * 3.0
+    del view
+    gc.collect()
+    c = host._result((1000, 1024))                  # slightly smaller request: same recycled block
+    assert c.ctypes.data == addr
+    small = host._result((4, 4))
+    assert small.base is None and not small.any()   # small results stay plain zeroed numpy arrays
+    with pytest.raises(ValueError):
+        _cabi.check(_cabi.lib().kmg_host_free(C.c_void_p(b.ctypes.data + 64)))
+    del b, c
+    gc.collect()
+    assert _cabi.lib().kmg_release() == 0
