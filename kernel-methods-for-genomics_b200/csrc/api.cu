@@ -219,16 +219,35 @@ void widen_s32_row(double* __restrict__ dst, const int32_t* __restrict__ src, in
     for (; j < n; ++j) dst[j] = (double)src[j];
 }
 
+void widen_u16_row(double* __restrict__ dst, const uint16_t* __restrict__ src, int64_t n) {
+    int64_t j = 0;
+#if defined(__SSE2__)
+    while (j < n && (reinterpret_cast<uintptr_t>(dst + j) & 15)) { dst[j] = (double)src[j]; ++j; }
+    const __m128i zero = _mm_setzero_si128();
+    for (; j + 8 <= n; j += 8) {
+        const __m128i v = _mm_loadu_si128(reinterpret_cast<const __m128i*>(src + j));
+        const __m128i lo = _mm_unpacklo_epi16(v, zero), hi = _mm_unpackhi_epi16(v, zero);
+        _mm_stream_pd(dst + j, _mm_cvtepi32_pd(lo));
+        _mm_stream_pd(dst + j + 2, _mm_cvtepi32_pd(_mm_shuffle_epi32(lo, 0xEE)));
+        _mm_stream_pd(dst + j + 4, _mm_cvtepi32_pd(hi));
+        _mm_stream_pd(dst + j + 6, _mm_cvtepi32_pd(_mm_shuffle_epi32(hi, 0xEE)));
+    }
+#endif
+    for (; j < n; ++j) dst[j] = (double)src[j];
+}
+
 // src: device, `rows` x `cols` contiguous, doubles or (src_s32) int32 counts that the copy threads widen to double on
 // the way into the caller's buffer -- an unnormalised spectrum Gram is integer valued, so shipping the tensor cores'
 // own s32 accumulators halves the PCIe bytes per entry.  dst: host doubles, row stride ldk.
-int d2h_rows(double* dst, int64_t ldk, const void* src_v, bool src_s32, int64_t cols, int64_t rows, cudaStream_t s) {
+// src_elem: 8 = doubles, 4 = s32 counts, 2 = u16 counts (both widened exactly).
+int d2h_rows(double* dst, int64_t ldk, const void* src_v, int src_elem, int64_t cols, int64_t rows, cudaStream_t s) {
+    const bool src_s32 = src_elem != 8;  // "needs widening"
     if (rows <= 0 || cols <= 0) return KMG_OK;
     std::lock_guard<std::mutex> lk(g_ring.mu);
     int rc = ring_init();
     if (rc) return rc;
     const char* src = static_cast<const char*>(src_v);
-    const size_t row_bytes = (size_t)cols * (src_s32 ? 4 : 8);
+    const size_t row_bytes = (size_t)cols * (size_t)src_elem;
     {
         // Freshly allocated numpy memory is first touched by the copy threads below; with transparent huge pages the
         // kernel zero-fills 2 MB at a time instead of taking a fault per 4 KB page.  Advisory: errors are ignored.
@@ -258,8 +277,10 @@ int d2h_rows(double* dst, int64_t ldk, const void* src_v, bool src_s32, int64_t 
         fut[slot] = std::async(std::launch::async, [=]() -> int {
             if (cudaEventSynchronize(ev) != cudaSuccess) return 1;
             if (src_s32) {
-                for (int64_t i = 0; i < nr; ++i)
-                    widen_s32_row(d0 + i * ldk, reinterpret_cast<const int32_t*>(stage + (size_t)i * row_bytes), cols);
+                for (int64_t i = 0; i < nr; ++i) {
+                    if (src_elem == 4) widen_s32_row(d0 + i * ldk, reinterpret_cast<const int32_t*>(stage + (size_t)i * row_bytes), cols);
+                    else widen_u16_row(d0 + i * ldk, reinterpret_cast<const uint16_t*>(stage + (size_t)i * row_bytes), cols);
+                }
 #if defined(__SSE2__)
                 _mm_sfence();
 #endif
@@ -308,6 +329,23 @@ typedef int (*BlockFn)(void* ctx, int64_t r0, int64_t rows, void* d_out, int64_t
 
 // Build an nr x nc Gram block-row by block-row on the device and copy it to host memory.
 // If the whole (square, symmetric) matrix fits it is built in one symmetric launch.
+// Second narrowing of a block of s32 counts for the link: if every entry fits 16 bits (checked on the device, exact)
+// the block crosses PCIe as u16 -- 2 bytes per Gram entry instead of 8.  Costs one HBM pass (6 B/entry) and a flag read.
+int try_narrow(const void* d_s32, int64_t count, DevBuf* narrow, int* elem, cudaStream_t s) {
+    if (getenv("KMG_D2H_S32")) return KMG_OK;
+    int rc;
+    DevBuf flag;
+    if ((rc = narrow->alloc((size_t)count * 2 + 16))) return rc;
+    if ((rc = flag.alloc(sizeof(int)))) return rc;
+    KMG_CUDA_CHECK(cudaMemsetAsync(flag.p, 0, sizeof(int), s));
+    if ((rc = kmg_ew_narrow_u16(static_cast<const int32_t*>(d_s32), count, narrow->as<uint16_t>(), flag.as<int>(), s))) return rc;
+    int h = 0;
+    KMG_CUDA_CHECK(cudaMemcpyAsync(&h, flag.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+    KMG_CUDA_CHECK(cudaStreamSynchronize(s));
+    if (h == 0) *elem = 2;
+    return KMG_OK;
+}
+
 // out_s32: `fn` writes int32 counts (d2h_rows widens them on the host side of the link).
 int build_to_host(int64_t nr, int64_t nc, bool symmetric, BlockFn fn, void* ctx, double* K, int64_t ldk, bool out_s32 = false) {
     if (nr == 0 || nc == 0) return KMG_OK;
@@ -323,7 +361,10 @@ int build_to_host(int64_t nr, int64_t nc, bool symmetric, BlockFn fn, void* ctx,
         kmg_trace("build_to_host: output allocated");
         if ((rc = fn(ctx, 0, nr, out.p, nc, symmetric ? 1 : 0, s0))) return rc;
         if (getenv("KMG_TRACE")) { cudaStreamSynchronize(s0); kmg_trace("build_to_host: kernel done"); }
-        rc = d2h_rows(K, ldk, out.p, out_s32, nc, nr, s0);
+        int elem = out_s32 ? 4 : 8;
+        DevBuf narrow;
+        if (out_s32 && (rc = try_narrow(out.p, nr * nc, &narrow, &elem, s0))) return rc;
+        rc = d2h_rows(K, ldk, elem == 2 ? narrow.p : out.p, elem, nc, nr, s0);
         kmg_trace("build_to_host: copied to host");
         return rc;
     }
@@ -340,7 +381,10 @@ int build_to_host(int64_t nr, int64_t nc, bool symmetric, BlockFn fn, void* ctx,
             const int64_t r1 = (b + 1) * br;
             if ((rc = fn(ctx, r1, std::min<int64_t>(br, nr - r1), buf[(b + 1) & 1].p, nc, 0, st[(b + 1) & 1]))) return rc;
         }
-        if ((rc = d2h_rows(K + r0 * ldk, ldk, buf[b & 1].p, out_s32, nc, rows, st[b & 1]))) return rc;
+        int elem = out_s32 ? 4 : 8;
+        DevBuf narrow;
+        if (out_s32 && (rc = try_narrow(buf[b & 1].p, rows * nc, &narrow, &elem, st[b & 1]))) return rc;
+        if ((rc = d2h_rows(K + r0 * ldk, ldk, elem == 2 ? narrow.p : buf[b & 1].p, elem, nc, rows, st[b & 1]))) return rc;
     }
     return KMG_OK;
 }

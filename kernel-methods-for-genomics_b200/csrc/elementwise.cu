@@ -169,7 +169,36 @@ __global__ void __launch_bounds__(256) weighted_dot_partial_kernel(const double*
     if (threadIdx.x == 0) partial[i] = acc * wi;
 }
 
+// s32 counts -> u16 for the host link (api.cu d2h_rows widens them back to double): 8 entries per thread, 16-byte
+// stores.  Any entry outside 0..65535 raises *flag and the caller ships the s32 block instead.
+__global__ void __launch_bounds__(256) narrow_u16_kernel(const int32_t* __restrict__ src, int64_t count, uint16_t* __restrict__ dst,
+                                                         int* __restrict__ flag) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x * 8;
+    uint32_t bad = 0;
+    for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 8; i < count; i += stride) {
+        if (i + 8 <= count) {
+            const int4 a = *reinterpret_cast<const int4*>(src + i), b = *reinterpret_cast<const int4*>(src + i + 4);
+            bad |= (uint32_t)(a.x | a.y | a.z | a.w | b.x | b.y | b.z | b.w);
+            uint4 o;
+            o.x = (uint32_t)a.x | ((uint32_t)a.y << 16); o.y = (uint32_t)a.z | ((uint32_t)a.w << 16);
+            o.z = (uint32_t)b.x | ((uint32_t)b.y << 16); o.w = (uint32_t)b.z | ((uint32_t)b.w << 16);
+            *reinterpret_cast<uint4*>(dst + i) = o;
+        } else {
+            for (int64_t j = i; j < count; ++j) { bad |= (uint32_t)src[j]; dst[j] = (uint16_t)src[j]; }
+        }
+    }
+    if (bad >> 16) atomicOr(flag, 1);  // negative values have the top bit set
+}
+
 }  // namespace
+
+int kmg_ew_narrow_u16(const int32_t* src, int64_t count, uint16_t* dst, int* flag, cudaStream_t s) {
+    if (count <= 0) return 0;
+    const int64_t blocks = std::min<int64_t>((count + 2047) / 2048, 148 * 16);
+    narrow_u16_kernel<<<(unsigned)blocks, 256, 0, s>>>(src, count, dst, flag);
+    KMG_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
 
 int kmg_ew_diag_sqrt(const double* K, int64_t n, int64_t ld, double* sd, cudaStream_t s) {
     if (n <= 0) return KMG_OK;

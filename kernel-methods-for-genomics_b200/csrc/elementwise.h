@@ -15,6 +15,8 @@ int kmg_ew_combine(const double* const* Ks, const int64_t* lds, const double* u,
 // result = sum_ij A_ij * (B ? B_ij : 1) * (w ? w_i w_j : 1);  partial: n doubles of scratch
 int kmg_ew_weighted_dot(const double* A, int64_t lda, const double* B, int64_t ldb, const double* w, int64_t n, double* partial,
                         double* result, cudaStream_t s);
+// s32 -> u16 (count % 1 == 0; src 16-byte, dst 16-byte aligned); *flag |= 1 when an entry does not fit
+int kmg_ew_narrow_u16(const int32_t* src, int64_t count, uint16_t* dst, int* flag, cudaStream_t s);
 int kmg_ew_row_sums(const double* K, int64_t rows, int64_t cols, int64_t ld, double* rs, cudaStream_t s);
 int64_t kmg_ew_col_sums_workspace(int64_t rows, int64_t cols);
 int kmg_ew_col_sums(const double* K, int64_t rows, int64_t cols, int64_t ld, double* cs, void* workspace, cudaStream_t s);

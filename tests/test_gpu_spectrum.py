@@ -152,6 +152,32 @@ def test_host_api_spectrum(kh, golden, dna):
         kh.spectrum_gram(["ACGT", "ACG"], 2)
 
 
+def test_host_link_transports(kh, dna, monkeypatch):
+    """The unnormalised counts cross PCIe as u16 when every entry of the block fits, as s32 otherwise, or as fp64
+    (KMG_D2H_F64): same bits in the caller's array either way.  Homopolymers at k=1..7 reach 67 256 > 65 535."""
+    codes, _ = dna
+    ks = [1, 2, 3, 4, 5, 6, 7]
+    c = codes[:700].copy()
+    want = onp.spectrum_gram(c, ks)
+    assert want.max() <= 65535
+    assert np.array_equal(kh.spectrum_gram(c, ks), want)                 # u16 link (large enough for a recycled block)
+    assert np.array_equal(kh.spectrum_gram(c[:300], ks, cols=c), want[:300])
+    c[3] = 0
+    c[11] = 0
+    want = onp.spectrum_gram(c, ks)
+    assert want[3, 11] == 67256
+    assert np.array_equal(kh.spectrum_gram(c, ks), want)                 # overflow detected on the device: s32 link
+    monkeypatch.setenv("KMG_D2H_S32", "1")
+    assert np.array_equal(kh.spectrum_gram(c, ks), want)
+    monkeypatch.setenv("KMG_D2H_F64", "1")
+    assert np.array_equal(kh.spectrum_gram(c, ks), want)
+    monkeypatch.setenv("KMG_DEVICE_BUDGET_BYTES", str(2 * 8 * 256 * 700))  # streamed block-rows, u16 and s32 blocks mixed
+    monkeypatch.delenv("KMG_D2H_F64")
+    monkeypatch.delenv("KMG_D2H_S32")
+    assert np.array_equal(kh.spectrum_gram(c, ks), want)
+    assert np.array_equal(kh.spectrum_gram(c[:300], ks, cols=c), want[:300])
+
+
 def test_full_size_properties(kd):
     """BASELINE-sized feature width (k=1..7) at n = 20 000: size-independent properties on device --
     symmetry, diagonal = sum of squares of Phi, row sums = Phi (Phi^T 1), and agreement of the two tile shapes."""

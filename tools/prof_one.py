@@ -31,6 +31,24 @@ elif a.kind == "mm":
 elif a.kind == "la":
     out = torch.empty((a.rows, a.cols), dtype=torch.float64, device="cuda")
     fn = lambda: kd.la_block(planes[:a.rows], planes[:a.cols], 101, 11, 1, 0.5, 0, out=out)
+elif a.kind == "all":
+    # one launch of every non-GEMM kernel on the path (ncu target for profiles/r1_*_ncu_summary.txt)
+    o1 = torch.empty((8192, 16384), dtype=torch.float64, device="cuda")
+    o2 = torch.empty((4096, 4096), dtype=torch.float64, device="cuda")
+    o3 = torch.empty((512, 4096), dtype=torch.float64, device="cuda")
+    sq = torch.rand((8192, 8192), dtype=torch.float64, device="cuda") + 1.0
+    def fn():
+        kd.wd_block(planes[:8192], planes[:16384], 101, 10, out=o1)
+        kd.wds_block(planes[:512], planes[:4096], 101, 3, 2, out=o3)
+        kd.mismatch_block(planes[:4096], planes[:4096], 101, 10, 1, out=o2)
+        kd.mismatch_block(planes[:4096], planes[:4096], 101, 6, 2, out=o2)
+        kd.la_block(planes[:512], planes[:4096], 101, 11, 1, 0.5, 0, out=o3)
+        kd.la_block(planes[:512], planes[:4096], 101, 11, 1, 0.5, 1, out=o3)
+        phi = kd.mismatch_phi(planes[:16384], 101, 6, 1)
+        kd.spectrum_phi(planes[:16384], 101, [1, 2, 3, 4, 5, 6, 7])
+        kd.normalize_(sq)
+        kd.center(sq)
+        kd.combine([sq, sq, sq], [0.2, 0.3, 0.5], 2)
 ts = []
 for _ in range(a.iters):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
