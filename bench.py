@@ -285,10 +285,11 @@ def main():
     if dist is not None:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e = {"value": e2e_rows * float(n) * world / float(te.item()), "unit": "entries/s",
-           "h2d_bytes_per_step": int((e2e_rows + n) * L), "d2h_bytes_per_step": int(e2e_rows * n * 4),
+           "h2d_bytes_per_step": int((e2e_rows + n) * L), "d2h_bytes_per_step": int(e2e_rows * n * (2 if float(Kh.max()) <= 65535.0 else 4)),
            "sample": f"{e2e_rows} x {n} rows of the block-row per GPU per call through kmg_spectrum_host (numpy in, numpy fp64 out; "
                      "pageable host memory; H2D of the sequences and D2H of the Gram inside the timed region; the counts cross "
-                     "PCIe as the GEMM's s32 accumulators and are widened to fp64 by the copy threads; result arrays come "
+                     "PCIe as u16 when every entry of the block fits (checked on the device), else as the GEMM's s32 accumulators, "
+                     "and are widened to fp64 by the copy threads; result arrays come "
                      "from libkmg's recycled host blocks, warm after the first call)",
            "first_call_value": e2e_rows * float(n) * world / cold_dt,
            "calls_timed": e2e_steps, "checksum": float(Kh[0, :8].sum())}

@@ -125,6 +125,23 @@ int kmg_phi_diag_sqrt_dev(const int8_t* d_phi, int64_t n, int64_t width, int64_t
 int kmg_gram_i8_dev(const int8_t* d_phi_rows, const int8_t* d_phi_cols, int64_t rows, int64_t cols, int64_t width,
                     int64_t ld_phi, int64_t row_index0, int64_t col_index0, void* d_out, int64_t ldo, int out_dtype,
                     int symmetric, const double* d_sd_rows, const double* d_sd_cols, int m_sub, void* stream);
+/* Symmetric Gram of ALL n rows of one Phi, cut into n_parts block-rows (one per GPU of a node; part_row0: n_parts+1
+ * boundaries, multiples of 256, last = n).  Part `part` computes about half of its block-row -- the blocks at cyclic
+ * distance < n_parts/2 plus the upper triangle of its diagonal block -- and its epilogue stores every tile twice: into
+ * part_out[part] and, transposed, into the block-row buffer of the part that owns the tile's columns (part_out[b]: peer
+ * device memory, e.g. from kmg_ipc_open).  After all parts have run (stream sync + barrier) every buffer holds its full
+ * rows_p x n block-row: the mirror of kernels.py:45 is the one exchange of the path and it rides the GEMM epilogue.
+ * d_sd (nullable): sqrt(diag) of all n rows, fused cosine normalisation.  computed_entries (nullable out). */
+int kmg_gram_i8_sharded_dev(const int8_t* d_phi, int64_t n, int64_t width, int64_t ld_phi, int n_parts, int part,
+                            const int64_t* part_row0, void* const* part_out, int64_t ldo, int out_dtype, const double* d_sd,
+                            int64_t* computed_entries, void* stream);
+/* the assignment rule itself (host utility, no GPU): 1 when part a computes tile (I, J) of the global 256-grid whose
+ * columns belong to part b; exactly one of a:(I,J) and b:(J,I) is 1 for I != J */
+int kmg_gram_sharded_takes_host(int n_parts, const int64_t* part_row0, int a, int b, int64_t I, int64_t J);
+/* CUDA IPC handles (64 bytes) of buffers from kmg_dev_malloc: one process per GPU, same node */
+int kmg_ipc_export(const void* d_ptr, uint8_t* handle64);
+int kmg_ipc_open(const uint8_t* handle64, void** d_ptr);
+int kmg_ipc_close(void* d_ptr);
 /* same contraction on CUDA cores (dp4a), s32 output: validation only, not a product path. */
 int kmg_gram_i8_simt_dev(const int8_t* d_phi_rows, const int8_t* d_phi_cols, int64_t rows, int64_t cols, int64_t width,
                          int64_t ld_phi, int32_t* d_out, int64_t ldo, void* stream);

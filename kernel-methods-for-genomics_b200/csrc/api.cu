@@ -927,6 +927,58 @@ int kmg_gram_i8_dev(const int8_t* d_phi_rows, const int8_t* d_phi_cols, int64_t 
     return kmg_gram_i8_launch(&a, (cudaStream_t)stream);
 }
 
+// Sharded symmetric spectrum Gram: part `part` of `n_parts` computes its share of the upper-triangle work
+// and stores each tile into its own block-row and, transposed, into the owner's block-row -- the one exchange step of
+// the path, done by the GEMM epilogue itself over NVLink peer memory instead of a collective afterwards.
+int kmg_gram_i8_sharded_dev(const int8_t* d_phi, int64_t n, int64_t width, int64_t ld_phi, int n_parts, int part,
+                            const int64_t* part_row0, void* const* part_out, int64_t ldo, int out_dtype, const double* d_sd,
+                            int64_t* computed_entries, void* stream) {
+    KMG_REQUIRE(out_dtype == KMG_OUT_S32 || out_dtype == KMG_OUT_F64, KMG_ERR_ARG, "gram_i8_sharded: bad out_dtype");
+    KMG_REQUIRE(!(d_sd && out_dtype != KMG_OUT_F64), KMG_ERR_ARG, "gram_i8_sharded: normalisation needs the f64 output");
+    KMG_REQUIRE(n_parts >= 1 && n_parts <= KMG_MAX_PARTS && part >= 0 && part < n_parts && part_row0 && part_out, KMG_ERR_ARG,
+                "gram_i8_sharded: 1..%d parts", KMG_MAX_PARTS);
+    KMG_REQUIRE(ldo >= n, KMG_ERR_ARG, "gram_i8_sharded: ldo < n");
+    if (computed_entries) *computed_entries = 0;
+    if (n == 0) return KMG_OK;
+    GramI8Args a;
+    memset(&a, 0, sizeof(a));
+    const int64_t r0 = part_row0[part];
+    a.phi_rows = d_phi + r0 * ld_phi; a.phi_cols = d_phi; a.rows = part_row0[part + 1] - r0; a.cols = n; a.Dpad = width; a.ld_phi = ld_phi;
+    a.row_index0 = r0; a.col_index0 = 0; a.out = part_out[part]; a.ldo = ldo; a.out_dtype = out_dtype;
+    a.sd_rows = d_sd ? d_sd + r0 : nullptr; a.sd_cols = d_sd;
+    a.n_parts = n_parts; a.part = part; a.part_row0 = part_row0; a.part_out = part_out; a.computed_entries = computed_entries;
+    return kmg_gram_i8_launch(&a, (cudaStream_t)stream);
+}
+
+int kmg_gram_sharded_takes_host(int n_parts, const int64_t* part_row0, int a, int b, int64_t I, int64_t J) {
+    KMG_REQUIRE(n_parts >= 1 && n_parts <= KMG_MAX_PARTS && part_row0 && a >= 0 && a < n_parts && b >= 0 && b < n_parts, KMG_ERR_ARG,
+                "gram_sharded_takes: bad arguments");
+    return kmg_gram_sharded_takes(n_parts, part_row0, a, b, I, J);
+}
+
+// ---- CUDA IPC: how the ranks of one node see each other's block-row buffers (cudaMalloc'ed by kmg_dev_malloc) ----
+int kmg_ipc_export(const void* d_ptr, uint8_t* handle64) {
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    KMG_REQUIRE(d_ptr && handle64, KMG_ERR_ARG, "ipc_export: null argument");
+    cudaIpcMemHandle_t h;
+    KMG_CUDA_CHECK(cudaIpcGetMemHandle(&h, const_cast<void*>(d_ptr)));
+    memcpy(handle64, &h, 64);
+    return KMG_OK;
+}
+
+int kmg_ipc_open(const uint8_t* handle64, void** d_ptr) {
+    KMG_REQUIRE(d_ptr && handle64, KMG_ERR_ARG, "ipc_open: null argument");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    KMG_CUDA_CHECK(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return KMG_OK;
+}
+
+int kmg_ipc_close(void* d_ptr) {
+    if (d_ptr) KMG_CUDA_CHECK(cudaIpcCloseMemHandle(d_ptr));
+    return KMG_OK;
+}
+
 int kmg_gram_i8_simt_dev(const int8_t* d_phi_rows, const int8_t* d_phi_cols, int64_t rows, int64_t cols, int64_t width,
                          int64_t ld_phi, int32_t* d_out, int64_t ldo, void* stream) {
     return kmg_gram_i8_simt_launch(d_phi_rows, d_phi_cols, ld_phi, rows, cols, width, d_out, ldo, (cudaStream_t)stream);

@@ -5,6 +5,7 @@
 
 #define KMG_OUT_S32 0
 #define KMG_OUT_F64 1
+#define KMG_MAX_PARTS 8  // power of two
 
 struct GramI8Args {
     const int8_t* phi_rows;  // first row of the row block of Phi (device)
@@ -24,7 +25,18 @@ struct GramI8Args {
     int m_sub;               // 0 = auto, 1 = 128x256 tiles, 2 = 256x256 tiles
     int max_ctas;            // 0 = all SMs
     int64_t* computed_entries;  // optional out: entries actually issued to the tensor cores
+    // Sharded symmetric build (n_parts > 0): the n x n Gram is cut into n_parts block-rows, one per GPU; this launch
+    // computes part `part`'s share of the upper-triangle work and stores every tile twice -- into its own block-row
+    // and, transposed, into the block-row of the part that owns the tile's columns (peer device memory).
+    // rows = the part's row count, cols = n, row_index0 = part_row0[part], col_index0 = 0; phi_cols = all of Phi.
+    int n_parts, part;
+    const int64_t* part_row0;  // host: n_parts + 1 boundaries, multiples of 256 except the last (= n)
+    void* const* part_out;     // host: device base pointer of every part's block-row buffer (row stride ldo)
 };
+
+// 1 when part `a` of `g` (boundaries part_row0, multiples of 256) computes tile (I, J) of the global 256 x 256 tile grid,
+// I in a's row tiles, J in the column tiles owned by part b; see gram_i8_tcgen05.cu
+int kmg_gram_sharded_takes(int g, const int64_t* part_row0, int a, int b, int64_t I, int64_t J);
 
 int kmg_gram_i8_launch(const GramI8Args* a, cudaStream_t stream);
 int kmg_gram_i8_simt_launch(const int8_t* A, const int8_t* B, int64_t ld, int64_t rows, int64_t cols, int64_t Dpad,

@@ -21,6 +21,7 @@
 #include <stdint.h>
 #include <stdlib.h>
 
+#include <array>
 #include <map>
 #include <mutex>
 #include <tuple>
@@ -54,11 +55,14 @@ struct KernelParams {
     int32_t out_dtype;  // KMG_OUT_S32 / KMG_OUT_F64
     void* out;
     int64_t ldo;
-    void* out_t;  // mirrored destination base (element (r,c) -> out_t[c*ldo_t + r]); may be null
+    // mirrored destinations: a tile with flag z stores element (r,c) (block-local indices) to mirror_base[w][c*ldo_t + r];
+    // w = 0 for a single symmetric block; in a sharded symmetric build w is the part that owns the tile's columns and
+    // mirror_base[w] its block-row buffer (peer device memory), pre-offset on the host so that local indices address it
+    void* mirror_base[KMG_MAX_PARTS];
     int64_t ldo_t;
     const double* sd_rows;  // sqrt(diag) per local row / col for cosine normalisation; null = raw
     const double* sd_cols;
-    const int4* tiles;  // {row_tile, col_tile, mirror, 0}
+    const int4* tiles;  // {row_tile, col_tile, mirror, destination part of the mirror store}
     uint32_t* wave_counter;  // grid-wide arrival counter (zeroed before the launch) or null
     uint64_t hint_a, hint_b;  // L2 eviction policy of the A / B operand loads
 };
@@ -100,7 +104,8 @@ __device__ __forceinline__ double u32_to_f64(uint32_t v) {
 
 template <bool INT_CVT>
 __device__ __forceinline__ void store_chunk(const KernelParams& p, const uint32_t (&v)[32], uint32_t* stage /*4 KB*/,
-                                            int lane, int64_t row_base, int64_t col0, bool mirror) {
+                                            int lane, int64_t row_base, int64_t col0, void* out_t) {
+    const bool mirror = out_t != nullptr;
     const int64_t ncol = (p.cols - col0 < 32) ? (p.cols - col0) : 32;  // warp-uniform, > 0
     int64_t nrow = p.rows - row_base;
     if (nrow > 32) nrow = 32;
@@ -149,11 +154,11 @@ __device__ __forceinline__ void store_chunk(const KernelParams& p, const uint32_
         if (mirror) {
             const int64_t row_t = row_base + lane;
             if (p.out_dtype == KMG_OUT_S32) {
-                int32_t* dt = reinterpret_cast<int32_t*>(p.out_t) + col0 * p.ldo_t + row_t;
+                int32_t* dt = reinterpret_cast<int32_t*>(out_t) + col0 * p.ldo_t + row_t;
 #pragma unroll
                 for (int j = 0; j < 32; ++j) { *dt = (int32_t)v[j]; dt += p.ldo_t; }
             } else {
-                double* dt = reinterpret_cast<double*>(p.out_t) + col0 * p.ldo_t + row_t;
+                double* dt = reinterpret_cast<double*>(out_t) + col0 * p.ldo_t + row_t;
 #pragma unroll
                 for (int j = 0; j < 32; ++j) { *dt = u32_to_f64<INT_CVT>(v[j]); dt += p.ldo_t; }
             }
@@ -176,7 +181,7 @@ __device__ __forceinline__ void store_chunk(const KernelParams& p, const uint32_
         }
         const int64_t row_t = row_base + lane;
         if (mirror && row_t < p.rows) {
-            int32_t* dt = reinterpret_cast<int32_t*>(p.out_t) + col0 * p.ldo_t + row_t;
+            int32_t* dt = reinterpret_cast<int32_t*>(out_t) + col0 * p.ldo_t + row_t;
 #pragma unroll
             for (int j = 0; j < 32; ++j)
                 if (j < ncol) dt[(int64_t)j * p.ldo_t] = (int32_t)v[j];
@@ -211,7 +216,7 @@ __device__ __forceinline__ void store_chunk(const KernelParams& p, const uint32_
         }
         const int64_t row_t = row_base + lane;
         if (mirror && row_t < p.rows) {
-            double* dt = reinterpret_cast<double*>(p.out_t) + col0 * p.ldo_t + row_t;
+            double* dt = reinterpret_cast<double*>(out_t) + col0 * p.ldo_t + row_t;
             const double sr = norm ? p.sd_rows[row_t] : 1.0;
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
@@ -340,7 +345,7 @@ gram_i8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         uint32_t acc = 0, acc_phase = 0;
         for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
             const int4 tile = p.tiles[t];
-            const bool mirror = tile.z != 0;
+            void* const mirror = tile.z != 0 ? p.mirror_base[tile.w & (KMG_MAX_PARTS - 1)] : nullptr;
             ptx::mbar_wait(&tfull[acc], acc_phase);
             ptx::tcgen05_fence_after();
 #pragma unroll
@@ -501,7 +506,7 @@ gram_i8_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         uint32_t acc = 0, acc_phase = 0;
         for (int t = cluster_id; t < p.ntiles; t += num_clusters) {
             const int4 tile = p.tiles[t];
-            const bool mirror = tile.z != 0;
+            void* const mirror = tile.z != 0 ? p.mirror_base[tile.w & (KMG_MAX_PARTS - 1)] : nullptr;
             ptx::mbar_wait(&tfull[acc], acc_phase);
             ptx::tcgen05_fence_after();
             const int64_t row_base = (int64_t)tile.x * C::BM + (int64_t)rank * 128 + quarter * 32;
@@ -588,8 +593,11 @@ int make_map(CUtensorMap* m, const int8_t* base, int64_t nrows, int64_t Dpad, in
 struct TileKey {
     int64_t rows, cols, r0, c0;
     int bm, sym, band;
+    int n_parts, part;
+    std::array<int64_t, KMG_MAX_PARTS + 1> bounds;  // part_row0 of a sharded build, zeros otherwise
     bool operator<(const TileKey& o) const {
-        return std::tie(rows, cols, r0, c0, bm, sym, band) < std::tie(o.rows, o.cols, o.r0, o.c0, o.bm, o.sym, o.band);
+        return std::tie(rows, cols, r0, c0, bm, sym, band, n_parts, part, bounds) <
+               std::tie(o.rows, o.cols, o.r0, o.c0, o.bm, o.sym, o.band, o.n_parts, o.part, o.bounds);
     }
 };
 
@@ -636,15 +644,23 @@ int get_tiles(const TileKey& key, cudaStream_t stream, TileList* out) {
         const int64_t b1 = (b0 + G < tm_n) ? b0 + G : tm_n;
         for (int64_t tn = 0; tn < tn_n; ++tn) {
             for (int64_t tm = b0; tm < b1; ++tm) {
-                int mirror = 0;
-                if (key.sym) {
+                int mirror = 0, dest = 0;
+                if (key.n_parts > 0) {
+                    // sharded symmetric build: global 256-grid tile (I, J); b = the part owning columns of J
+                    const int64_t I = key.r0 / BM + tm, J = tn;
+                    int b = 0;
+                    while (b + 1 < key.n_parts && J * BN >= key.bounds[b + 1]) ++b;
+                    if (!kmg_gram_sharded_takes(key.n_parts, key.bounds.data(), key.part, b, I, J)) continue;
+                    mirror = (I != J) ? 1 : 0;
+                    dest = b;
+                } else if (key.sym) {
                     // global index ranges of this tile
                     const int64_t rlo = key.r0 + tm * BM, rhi = rlo + BM - 1;
                     const int64_t clo = key.c0 + tn * BN, chi = clo + BN - 1;
                     if (chi < rlo) continue;        // entirely below the diagonal: produced by a mirror store
                     mirror = (clo > rhi) ? 1 : 0;   // entirely above: its transpose is nobody's tile
                 }
-                tiles.push_back(make_int4((int)tm, (int)tn, mirror, 0));
+                tiles.push_back(make_int4((int)tm, (int)tn, mirror, dest));
                 const int64_t rr = (key.rows - tm * BM < BM) ? key.rows - tm * BM : BM;
                 const int64_t cc = (key.cols - tn * BN < BN) ? key.cols - tn * BN : BN;
                 entries += rr * cc;
@@ -723,6 +739,25 @@ int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const KernelPara
 
 }  // namespace
 
+// Which part computes tile (I, J), I != J, of the symmetric Gram when its rows belong to part a and its columns to part
+// b: exactly one of (I, J) [by a] and (J, I) [by b] is computed, the other arrives as the mirror store.
+//   a == b            : the upper triangle, J >= I (as in the single-GPU symmetric build)
+//   cyclic distance d = (b - a) mod g:  2d < g -> a computes the whole block (a, b);  2d > g -> b does
+//   2d == g (g even)  : the block is split between the two parts by row tile so that every part computes g/2 blocks:
+//                       the lower-numbered part takes its first half of row tiles, the other one the transposes of the rest
+int kmg_gram_sharded_takes(int g, const int64_t* part_row0, int a, int b, int64_t I, int64_t J) {
+    if (a == b) return J >= I;
+    const int d = ((b - a) % g + g) % g;
+    if (2 * d < g) return 1;
+    if (2 * d > g) return 0;
+    // distance g/2: lo = min(a, b) splits ITS row tiles; lo computes (I, J) for I in its first half, hi computes the
+    // transposed tiles (J', I') of the rest, i.e. the tiles whose COLUMN tile lies in lo's second half
+    const int lo = a < b ? a : b;
+    const int64_t lo0 = part_row0[lo] / 256, lon = (part_row0[lo + 1] - part_row0[lo] + 255) / 256;
+    const int64_t half = (lon + 1) / 2;
+    return a < b ? (I - lo0) < half : (J - lo0) >= half;
+}
+
 int kmg_gram_i8_launch(const GramI8Args* a, cudaStream_t stream) {
     KMG_REQUIRE(a->rows > 0 && a->cols > 0, KMG_ERR_ARG, "gram_i8: empty block");
     KMG_REQUIRE(a->Dpad > 0 && a->Dpad % BK == 0, KMG_ERR_ARG, "gram_i8: Dpad (%lld) must be a positive multiple of %d",
@@ -731,7 +766,7 @@ int kmg_gram_i8_launch(const GramI8Args* a, cudaStream_t stream) {
     KMG_REQUIRE((reinterpret_cast<uintptr_t>(a->phi_rows) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->phi_cols) & 15) == 0,
                 KMG_ERR_ARG, "gram_i8: Phi must be 16-byte aligned");
     KMG_REQUIRE(a->rows < (1ll << 31) && a->cols < (1ll << 31), KMG_ERR_ARG, "gram_i8: block too large");
-    KMG_REQUIRE(!a->symmetric || a->out_t != nullptr, KMG_ERR_ARG, "gram_i8: symmetric needs a mirror destination");
+    KMG_REQUIRE(!a->symmetric || a->n_parts > 0 || a->out_t != nullptr, KMG_ERR_ARG, "gram_i8: symmetric needs a mirror destination");
     int m_sub = a->m_sub;
     static const int default_variant = env_int("KMG_GEMM_VARIANT", 0);
     if (m_sub == 0) m_sub = default_variant;
@@ -753,7 +788,22 @@ int kmg_gram_i8_launch(const GramI8Args* a, cudaStream_t stream) {
     static const int band = env_int("KMG_GEMM_BAND", 8);
     static const int sync_waves = env_int("KMG_GEMM_SYNC", 1);
     static const int hint_mode = env_int("KMG_GEMM_HINT", 0);
-    TileKey key{a->rows, a->cols, a->row_index0, a->col_index0, BM, a->symmetric ? 1 : 0, band > 0 ? band : 8};
+    const bool sharded = a->n_parts > 0;
+    TileKey key{a->rows, a->cols, a->row_index0, a->col_index0, BM, (a->symmetric && !sharded) ? 1 : 0, band > 0 ? band : 8, 0, 0, {}};
+    if (sharded) {
+        KMG_REQUIRE(pair, KMG_ERR_ARG, "gram_i8: the sharded symmetric build uses the CTA-pair kernel (m_sub 0 or 3)");
+        KMG_REQUIRE(a->n_parts <= KMG_MAX_PARTS && a->part >= 0 && a->part < a->n_parts && a->part_row0 && a->part_out,
+                    KMG_ERR_ARG, "gram_i8: bad sharding (1..%d parts)", KMG_MAX_PARTS);
+        for (int q = 0; q <= a->n_parts; ++q) {
+            KMG_REQUIRE(q == a->n_parts || a->part_row0[q] % 256 == 0, KMG_ERR_ARG, "gram_i8: part boundaries must be multiples of 256");
+            KMG_REQUIRE(q == 0 || a->part_row0[q] > a->part_row0[q - 1], KMG_ERR_ARG, "gram_i8: part boundaries must increase");
+            key.bounds[q] = a->part_row0[q];
+        }
+        KMG_REQUIRE(a->part_row0[0] == 0 && a->part_row0[a->n_parts] == a->cols && a->col_index0 == 0 &&
+                    a->row_index0 == a->part_row0[a->part] && a->rows == a->part_row0[a->part + 1] - a->part_row0[a->part],
+                    KMG_ERR_ARG, "gram_i8: block shape does not match the sharding");
+        key.n_parts = a->n_parts; key.part = a->part;
+    }
     TileList tl;
     rc = get_tiles(key, stream, &tl);
     if (rc) return rc;
@@ -767,7 +817,16 @@ int kmg_gram_i8_launch(const GramI8Args* a, cudaStream_t stream) {
     p.ntiles = tl.n;
     p.out_dtype = a->out_dtype;
     p.out = a->out; p.ldo = a->ldo;
-    p.out_t = a->symmetric ? a->out_t : nullptr; p.ldo_t = a->ldo_t;
+    for (int q = 0; q < KMG_MAX_PARTS; ++q) p.mirror_base[q] = nullptr;
+    p.ldo_t = a->ldo_t;
+    if (sharded) {
+        const int64_t esz = a->out_dtype == KMG_OUT_F64 ? 8 : 4;
+        p.ldo_t = a->ldo;
+        for (int q = 0; q < a->n_parts; ++q)  // element (r_local, c_global) -> part q's buffer [c_global - row0_q][row_index0 + r_local]
+            p.mirror_base[q] = static_cast<char*>(a->part_out[q]) + (a->row_index0 - a->part_row0[q] * a->ldo) * esz;
+    } else if (a->symmetric) {
+        p.mirror_base[0] = a->out_t;
+    }
     p.sd_rows = a->sd_rows; p.sd_cols = a->sd_cols;
     p.tiles = tl.dev;
     p.wave_counter = nullptr;

@@ -59,6 +59,11 @@ PROTOTYPES = {
     "kmg_mismatch_phi_dev": (_i32, [_vp, _i64, _i32, _i32, _i32, _vp, _i64, _vp]),
     "kmg_phi_diag_sqrt_dev": (_i32, [_vp, _i64, _i64, _i64, _vp, _vp]),
     "kmg_gram_i8_dev": (_i32, [_vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _vp, _i64, _i32, _i32, _vp, _vp, _i32, _vp]),
+    "kmg_gram_i8_sharded_dev": (_i32, [_vp, _i64, _i64, _i64, _i32, _i32, _vp, _vp, _i64, _i32, _vp, _vp, _vp]),
+    "kmg_gram_sharded_takes_host": (_i32, [_i32, _vp, _i32, _i32, _i64, _i64]),
+    "kmg_ipc_export": (_i32, [_vp, _vp]),
+    "kmg_ipc_open": (_i32, [_vp, _vp]),
+    "kmg_ipc_close": (_i32, [_vp]),
     "kmg_gram_i8_simt_dev": (_i32, [_vp, _vp, _i64, _i64, _i64, _i64, _vp, _i64, _vp]),
     "kmg_mismatch_dev": (_i32, [_vp, _vp, _i64, _i64, _i64, _i64, _i32, _i32, _i32, _vp, _i64, _i32, _i32, _vp, _vp, _vp]),
     "kmg_mismatch_diag_dev": (_i32, [_vp, _i64, _i32, _i32, _i32, _vp, _vp]),

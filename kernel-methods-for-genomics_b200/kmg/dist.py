@@ -12,6 +12,10 @@ only where the path has a real exchange:
                      and the grand sum are one all-reduce of n + 1 doubles;
   * frobenius_sharded  ALIGNF's <K_i, K_j>_F style reductions: one all-reduce of a scalar per pair.
 
+  * SymmetricShards  the mirror K[j,i] = K[i,j] (kernels.py:45) across GPUs: each rank computes only half of its
+                     block-row and the GEMM epilogue stores every tile twice, into its own buffer and -- transposed, over
+                     NVLink peer memory (CUDA IPC) -- into the owner's; no collective, one barrier at the end.
+
 The partition / collective logic is backend agnostic (it is what the gloo tests cover); the arithmetic is supplied
 by the caller: `kmg.device` functions on the GPU, oracle functions in the CPU tests.
 """
@@ -109,3 +113,90 @@ def mismatch_block_row(planes, L, k, m, n, normalize=True, group=None):
 def center_block_row(block, n, group=None):
     from . import device as kd
     return center_sharded(block, n, kd.row_sums, kd.col_sums, kd.center_apply, group)
+
+
+# ------------------------------------------------------------------------------------------------
+# Sharded SYMMETRIC build: half the tensor-core work per GPU, mirror stores over peer memory
+# ------------------------------------------------------------------------------------------------
+def sym_bounds(n, world, align=TILE_ALIGN):
+    """Boundaries of `world` non-empty block-rows, multiples of `align` (except the last, = n), balanced to one tile."""
+    tiles = -(-n // align)
+    if tiles < world:
+        raise ValueError(f"n = {n} is too small for {world} block-rows of at least {align} rows")
+    return [min(n, align * (p * tiles // world)) for p in range(world)] + [n]
+
+
+def sym_takes(bounds, a, b, I, J):
+    """The assignment rule (kmg_gram_sharded_takes_host): does part a compute tile (I, J) whose columns part b owns?"""
+    import ctypes as C
+    import numpy as np
+    from . import _cabi
+    bd = np.ascontiguousarray(bounds, np.int64)
+    return _cabi.check(_cabi.lib().kmg_gram_sharded_takes_host(len(bounds) - 1, bd.ctypes.data_as(C.c_void_p), a, b, I, J))
+
+
+class SymmetricShards:
+    """Block-row buffers of one n x n fp64 (or s32) Gram, one per rank of a single node, each visible to every other rank
+    through CUDA IPC.  `build_spectrum` fills them with the sharded symmetric GEMM."""
+
+    def __init__(self, n, dtype=torch.float64, group=None):
+        import ctypes as C
+        from . import _cabi
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.n, self.dtype = n, dtype
+        self.bounds = sym_bounds(n, self.world)
+        self.r0, self.r1 = self.bounds[self.rank], self.bounds[self.rank + 1]
+        esz = 8 if dtype == torch.float64 else 4
+        lib = _cabi.lib()
+        self._own = C.c_void_p()
+        _cabi.check(lib.kmg_dev_malloc((self.r1 - self.r0) * n * esz, C.byref(self._own)))
+        handle = (C.c_uint8 * 64)()
+        self.ptrs = [None] * self.world
+        self._opened = []
+        if self.world > 1:
+            _cabi.check(lib.kmg_ipc_export(self._own, handle))
+            handles = [None] * self.world
+            dist.all_gather_object(handles, bytes(handle), group=group)
+            for r, h in enumerate(handles):
+                if r == self.rank:
+                    continue
+                p = C.c_void_p()
+                _cabi.check(lib.kmg_ipc_open((C.c_uint8 * 64).from_buffer_copy(h), C.byref(p)))
+                self.ptrs[r] = p.value
+                self._opened.append(p)
+        self.ptrs[self.rank] = self._own.value
+        # this rank's block-row as a tensor (no copy): torch reads the CUDA array interface
+        holder = type("_Buf", (), {})()
+        holder.__cuda_array_interface__ = {"shape": (self.r1 - self.r0, n), "typestr": "<f8" if esz == 8 else "<i4",
+                                           "data": (self._own.value, False), "version": 3}
+        self._holder = holder
+        self.block = torch.as_tensor(holder, device=torch.device("cuda", torch.cuda.current_device()))
+
+    def build_spectrum(self, phi, sd=None):
+        """All ranks call this with their local copy of Phi (n x W int8).  Returns entries this rank issued to the MMA."""
+        from . import device as kd
+        computed = kd.gram_i8_sharded(phi, self.bounds, self.rank, self.ptrs, self.n,
+                                      out_dtype=1 if self.dtype == torch.float64 else 0, sd=sd)
+        return computed
+
+    def finish(self):
+        """Every buffer is complete once every rank's launch has finished: stream sync, then a barrier."""
+        torch.cuda.synchronize()
+        if self.world > 1:
+            dist.barrier(group=self.group)
+
+    def close(self):
+        from . import _cabi
+        lib = _cabi.lib()
+        self.block = None
+        if self.world > 1:
+            torch.cuda.synchronize()
+            dist.barrier(group=self.group)  # nobody still writes into a buffer that is about to be unmapped
+        for p in self._opened:
+            lib.kmg_ipc_close(p)
+        self._opened = []
+        if self._own is not None and self._own.value:
+            lib.kmg_dev_free(self._own)
+            self._own = None

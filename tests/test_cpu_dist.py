@@ -86,3 +86,31 @@ def test_block_rows_partition_properties():
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
             assert all(r0 % 256 == 0 or r0 == n for r0, _ in spans)
     assert kdist.all_block_rows(200_000, 8) == [(i * 25088, min(200_000, (i + 1) * 25088)) for i in range(8)]
+
+
+def test_symmetric_shard_assignment_covers_every_tile_once():
+    """kmg_gram_sharded_takes_host (the rule the sharded symmetric GEMM builds its tile lists from): for every pair of
+    tiles (I, J), I != J, exactly one of part(I) computing (I, J) and part(J) computing (J, I) holds; diagonal tiles are
+    computed by their owner; every part does about half of its block-row."""
+    from kmg import dist as kdist
+    for n, world in ((2048, 2), (3000, 2), (3000, 3), (5000, 4), (7000, 5), (200000 // 8, 8), (9000, 8), (4096, 1)):
+        bounds = kdist.sym_bounds(n, world)
+        assert bounds[0] == 0 and bounds[-1] == n and all(b % 256 == 0 for b in bounds[:-1])
+        assert all(bounds[p + 1] > bounds[p] for p in range(world))
+        tiles = -(-n // 256)
+        owner = [max(p for p in range(world) if bounds[p] <= 256 * t) for t in range(tiles)]
+        done = np.zeros((world,), np.int64)
+        for I in range(tiles):
+            for J in range(tiles):
+                t = kdist.sym_takes(bounds, owner[I], owner[J], I, J)
+                if I == J:
+                    assert t == 1
+                elif I < J:
+                    assert t + kdist.sym_takes(bounds, owner[J], owner[I], J, I) == 1, (n, world, I, J)
+                done[owner[I]] += t
+        rows = np.array([sum(1 for t in range(tiles) if owner[t] == p) for p in range(world)])
+        share = done / (rows * tiles)
+        if world > 1 and tiles >= 8 * world:
+            assert share.min() > 0.40 and share.max() < 0.62, (n, world, share)
+    with pytest.raises(ValueError):
+        kdist.sym_bounds(500, 4)

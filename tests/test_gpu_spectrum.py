@@ -178,6 +178,39 @@ def test_host_link_transports(kh, dna, monkeypatch):
     assert np.array_equal(kh.spectrum_gram(c[:300], ks, cols=c), want[:300])
 
 
+@pytest.mark.parametrize("world", [1, 2, 3, 4, 8])
+def test_sharded_symmetric_gram_single_device(kd, world):
+    """kmg_gram_i8_sharded_dev with every part's buffer on this one GPU: each part's launch computes about half of its
+    block-row and mirror-stores the rest into the other parts' buffers; together they must equal the plain Gram."""
+    import torch
+    from kmg import dist as kdist
+    n = 3000 if world < 8 else 2300
+    c = onp.synthetic_codes(n, 101, seed=3)
+    planes = kd.pack(c, 0)
+    for ks, dt in (([3], 1), (list(range(1, 8)), 1), ([1, 2, 3, 4, 5, 6, 7], 0)):
+        phi = kd.spectrum_phi(planes, 101, ks)
+        ref = kd.gram_i8(phi, phi, out_dtype=dt)
+        bounds = kdist.sym_bounds(n, world)
+        bufs = [torch.full((bounds[p + 1] - bounds[p], n), -7, dtype=ref.dtype, device="cuda") for p in range(world)]
+        ptrs = [b.data_ptr() for b in bufs]
+        computed = [kd.gram_i8_sharded(phi, bounds, p, ptrs, n, out_dtype=dt) for p in range(world)]
+        torch.cuda.synchronize()
+        assert torch.equal(torch.cat(bufs), ref), (world, ks, dt)
+        if world > 1:
+            assert sum(computed) < 0.62 * n * n
+            assert all(computed[p] < 0.75 * (bounds[p + 1] - bounds[p]) * n for p in range(world)), computed
+    # fused cosine normalisation through the mirror stores (kernels.py:398-415)
+    phi = kd.spectrum_phi(planes, 101, [4])
+    sd = kd.phi_diag_sqrt(phi)
+    ref = kd.gram_i8(phi, phi, symmetric=True, sd_rows=sd, sd_cols=sd)
+    bounds = kdist.sym_bounds(n, world)
+    bufs = [torch.zeros((bounds[p + 1] - bounds[p], n), dtype=torch.float64, device="cuda") for p in range(world)]
+    for p in range(world):
+        kd.gram_i8_sharded(phi, bounds, p, [b.data_ptr() for b in bufs], n, sd=sd)
+    torch.cuda.synchronize()
+    assert torch.equal(torch.cat(bufs), ref)
+
+
 def test_full_size_properties(kd):
     """BASELINE-sized feature width (k=1..7) at n = 20 000: size-independent properties on device --
     symmetry, diagonal = sum of squares of Phi, row sums = Phi (Phi^T 1), and agreement of the two tile shapes."""
