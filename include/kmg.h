@@ -127,14 +127,18 @@ int kmg_gram_i8_dev(const int8_t* d_phi_rows, const int8_t* d_phi_cols, int64_t 
                     int symmetric, const double* d_sd_rows, const double* d_sd_cols, int m_sub, void* stream);
 /* Symmetric Gram of ALL n rows of one Phi, cut into n_parts block-rows (one per GPU of a node; part_row0: n_parts+1
  * boundaries, multiples of 256, last = n).  Part `part` computes about half of its block-row -- the blocks at cyclic
- * distance < n_parts/2 plus the upper triangle of its diagonal block -- and its epilogue stores every tile twice: into
+ * distance < n_parts/2 plus the upper triangle of its diagonal block -- and delivers every tile twice: into
  * part_out[part] and, transposed, into the block-row buffer of the part that owns the tile's columns (part_out[b]: peer
  * device memory, e.g. from kmg_ipc_open).  After all parts have run (stream sync + barrier) every buffer holds its full
- * rows_p x n block-row: the mirror of kernels.py:45 is the one exchange of the path and it rides the GEMM epilogue.
+ * rows_p x n block-row: the mirror of kernels.py:45 is the one exchange of the path.
+ * d_stage: local staging of kmg_gram_sharded_stage_bytes bytes -- one GEMM launch per peer block writes the transposed
+ * block there and one pitched peer copy per block ships it while the next launch runs; NULL: a single launch whose
+ * epilogue stores into the peers' buffers directly (buffers on one device, or tests).
  * d_sd (nullable): sqrt(diag) of all n rows, fused cosine normalisation.  computed_entries (nullable out). */
+int kmg_gram_sharded_stage_bytes(int n_parts, const int64_t* part_row0, int part, int out_dtype, int64_t* bytes);
 int kmg_gram_i8_sharded_dev(const int8_t* d_phi, int64_t n, int64_t width, int64_t ld_phi, int n_parts, int part,
                             const int64_t* part_row0, void* const* part_out, int64_t ldo, int out_dtype, const double* d_sd,
-                            int64_t* computed_entries, void* stream);
+                            void* d_stage, int64_t* computed_entries, void* stream);
 /* the assignment rule itself (host utility, no GPU): 1 when part a computes tile (I, J) of the global 256-grid whose
  * columns belong to part b; exactly one of a:(I,J) and b:(J,I) is 1 for I != J */
 int kmg_gram_sharded_takes_host(int n_parts, const int64_t* part_row0, int a, int b, int64_t I, int64_t J);

@@ -928,11 +928,48 @@ int kmg_gram_i8_dev(const int8_t* d_phi_rows, const int8_t* d_phi_cols, int64_t 
 }
 
 // Sharded symmetric spectrum Gram: part `part` of `n_parts` computes its share of the upper-triangle work
-// and stores each tile into its own block-row and, transposed, into the owner's block-row -- the one exchange step of
-// the path, done by the GEMM epilogue itself over NVLink peer memory instead of a collective afterwards.
+// and delivers every tile twice -- into its own block-row and, transposed, into the block-row of the part that owns the
+// tile's columns: the mirror of kernels.py:45 is the one exchange step of the path.
+//   d_stage == NULL : one launch; the GEMM epilogue stores the transposed tiles straight into the owners' buffers (peer
+//                     memory).  Right for buffers on one device; over NVLink the scattered 256-byte stores cap the
+//                     kernel (2 GPUs, n = 100 000: 40.5 ms against 30.1 ms with both buffers local).
+//   d_stage != NULL : one launch per peer block (cyclic distance 1, 2, ...) whose epilogue writes the transposed block
+//                     contiguously into local staging, each followed by ONE pitched peer copy on the copy stream while
+//                     the next block's GEMM runs; the diagonal block (local mirror) goes last and hides the final copy.
+namespace {
+struct SubBlock { int b; int64_t r_lo, r_hi, c_lo, c_hi; };
+void sharded_plan(int g, const int64_t* bounds, int a, std::vector<SubBlock>* out) {
+    const int64_t a0 = bounds[a], a1 = bounds[a + 1];
+    for (int d = 1; d < g; ++d) {
+        const int b = (a + d) % g;
+        const int64_t b0 = bounds[b], b1 = bounds[b + 1];
+        if (2 * d < g) { out->push_back({b, a0, a1, b0, b1}); continue; }
+        if (2 * d > g) continue;
+        // distance g/2: split by the lower-numbered part's row tiles, as kmg_gram_sharded_takes does
+        const int lo = a < b ? a : b;
+        const int64_t lon = (bounds[lo + 1] - bounds[lo] + 255) / 256;
+        const int64_t split = std::min<int64_t>(bounds[lo] + (lon + 1) / 2 * 256, bounds[lo + 1]);
+        if (a < b) { if (split > a0) out->push_back({b, a0, split, b0, b1}); }
+        else if (split < b1) out->push_back({b, a0, a1, split, b1});
+    }
+}
+size_t stage_align(size_t x) { return (x + 255) & ~(size_t)255; }
+}  // namespace
+
+int kmg_gram_sharded_stage_bytes(int n_parts, const int64_t* part_row0, int part, int out_dtype, int64_t* bytes) {
+    KMG_REQUIRE(n_parts >= 1 && n_parts <= KMG_MAX_PARTS && part_row0 && part >= 0 && part < n_parts && bytes, KMG_ERR_ARG,
+                "gram_sharded_stage_bytes: bad arguments");
+    std::vector<SubBlock> plan;
+    sharded_plan(n_parts, part_row0, part, &plan);
+    size_t total = 0;
+    for (const SubBlock& sb : plan) total += stage_align((size_t)(sb.r_hi - sb.r_lo) * (size_t)(sb.c_hi - sb.c_lo) * (out_dtype == KMG_OUT_F64 ? 8 : 4));
+    *bytes = (int64_t)total;
+    return KMG_OK;
+}
+
 int kmg_gram_i8_sharded_dev(const int8_t* d_phi, int64_t n, int64_t width, int64_t ld_phi, int n_parts, int part,
                             const int64_t* part_row0, void* const* part_out, int64_t ldo, int out_dtype, const double* d_sd,
-                            int64_t* computed_entries, void* stream) {
+                            void* d_stage, int64_t* computed_entries, void* stream) {
     KMG_REQUIRE(out_dtype == KMG_OUT_S32 || out_dtype == KMG_OUT_F64, KMG_ERR_ARG, "gram_i8_sharded: bad out_dtype");
     KMG_REQUIRE(!(d_sd && out_dtype != KMG_OUT_F64), KMG_ERR_ARG, "gram_i8_sharded: normalisation needs the f64 output");
     KMG_REQUIRE(n_parts >= 1 && n_parts <= KMG_MAX_PARTS && part >= 0 && part < n_parts && part_row0 && part_out, KMG_ERR_ARG,
@@ -940,14 +977,64 @@ int kmg_gram_i8_sharded_dev(const int8_t* d_phi, int64_t n, int64_t width, int64
     KMG_REQUIRE(ldo >= n, KMG_ERR_ARG, "gram_i8_sharded: ldo < n");
     if (computed_entries) *computed_entries = 0;
     if (n == 0) return KMG_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int64_t a0 = part_row0[part], a1 = part_row0[part + 1];
+    const int64_t esz = out_dtype == KMG_OUT_F64 ? 8 : 4;
     GramI8Args a;
+    if (d_stage == nullptr) {
+        memset(&a, 0, sizeof(a));
+        a.phi_rows = d_phi + a0 * ld_phi; a.phi_cols = d_phi; a.rows = a1 - a0; a.cols = n; a.Dpad = width; a.ld_phi = ld_phi;
+        a.row_index0 = a0; a.col_index0 = 0; a.out = part_out[part]; a.ldo = ldo; a.out_dtype = out_dtype;
+        a.sd_rows = d_sd ? d_sd + a0 : nullptr; a.sd_cols = d_sd;
+        a.n_parts = n_parts; a.part = part; a.part_row0 = part_row0; a.part_out = part_out; a.computed_entries = computed_entries;
+        return kmg_gram_i8_launch(&a, s);
+    }
+    for (int q = 0; q <= n_parts; ++q)
+        KMG_REQUIRE((q == n_parts ? part_row0[q] == n : part_row0[q] % 256 == 0) && (q == 0 ? part_row0[0] == 0 : part_row0[q] > part_row0[q - 1]),
+                    KMG_ERR_ARG, "gram_i8_sharded: part boundaries must start at 0, increase in multiples of 256 and end at n");
+    int rc;
+    cudaStream_t s0, copy;
+    if ((rc = get_streams(&s0, &copy))) return rc;
+    std::vector<SubBlock> plan;
+    sharded_plan(n_parts, part_row0, part, &plan);
+    char* my = static_cast<char*>(part_out[part]);
+    char* stage = static_cast<char*>(d_stage);
+    int64_t total = 0, got = 0;
+    cudaEvent_t ev;
+    for (const SubBlock& sb : plan) {
+        const int64_t rows = sb.r_hi - sb.r_lo, cols = sb.c_hi - sb.c_lo;
+        memset(&a, 0, sizeof(a));
+        a.phi_rows = d_phi + sb.r_lo * ld_phi; a.phi_cols = d_phi + sb.c_lo * ld_phi; a.rows = rows; a.cols = cols; a.Dpad = width; a.ld_phi = ld_phi;
+        a.row_index0 = sb.r_lo; a.col_index0 = sb.c_lo; a.out = my + ((sb.r_lo - a0) * ldo + sb.c_lo) * esz; a.ldo = ldo; a.out_dtype = out_dtype;
+        a.sd_rows = d_sd ? d_sd + sb.r_lo : nullptr; a.sd_cols = d_sd ? d_sd + sb.c_lo : nullptr;
+        a.mirror_all = 1; a.out_t = stage; a.ldo_t = rows; a.computed_entries = &got;
+        if ((rc = kmg_gram_i8_launch(&a, s))) return rc;
+        total += got;
+        // the transposed block (cols x rows, contiguous) -> rows [c_lo, c_hi) x columns [r_lo, r_hi) of the owner's block-row
+        KMG_CUDA_CHECK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        KMG_CUDA_CHECK(cudaEventRecord(ev, s));
+        KMG_CUDA_CHECK(cudaStreamWaitEvent(copy, ev, 0));
+        KMG_CUDA_CHECK(cudaEventDestroy(ev));
+        char* dst = static_cast<char*>(part_out[sb.b]) + ((sb.c_lo - part_row0[sb.b]) * ldo + sb.r_lo) * esz;
+        KMG_CUDA_CHECK(cudaMemcpy2DAsync(dst, (size_t)(ldo * esz), stage, (size_t)(rows * esz), (size_t)(rows * esz), (size_t)cols,
+                                         cudaMemcpyDefault, copy));
+        stage += stage_align((size_t)(rows * cols * esz));
+    }
+    // diagonal block: the single-GPU symmetric build on this part's own square
     memset(&a, 0, sizeof(a));
-    const int64_t r0 = part_row0[part];
-    a.phi_rows = d_phi + r0 * ld_phi; a.phi_cols = d_phi; a.rows = part_row0[part + 1] - r0; a.cols = n; a.Dpad = width; a.ld_phi = ld_phi;
-    a.row_index0 = r0; a.col_index0 = 0; a.out = part_out[part]; a.ldo = ldo; a.out_dtype = out_dtype;
-    a.sd_rows = d_sd ? d_sd + r0 : nullptr; a.sd_cols = d_sd;
-    a.n_parts = n_parts; a.part = part; a.part_row0 = part_row0; a.part_out = part_out; a.computed_entries = computed_entries;
-    return kmg_gram_i8_launch(&a, (cudaStream_t)stream);
+    a.phi_rows = d_phi + a0 * ld_phi; a.phi_cols = a.phi_rows; a.rows = a1 - a0; a.cols = a1 - a0; a.Dpad = width; a.ld_phi = ld_phi;
+    a.row_index0 = a0; a.col_index0 = a0; a.out = my + a0 * esz; a.ldo = ldo; a.out_dtype = out_dtype;
+    a.symmetric = 1; a.out_t = a.out; a.ldo_t = ldo;
+    a.sd_rows = d_sd ? d_sd + a0 : nullptr; a.sd_cols = a.sd_rows; a.computed_entries = &got;
+    if ((rc = kmg_gram_i8_launch(&a, s))) return rc;
+    total += got;
+    // `stream` completes only after the peer copies have
+    KMG_CUDA_CHECK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    KMG_CUDA_CHECK(cudaEventRecord(ev, copy));
+    KMG_CUDA_CHECK(cudaStreamWaitEvent(s, ev, 0));
+    KMG_CUDA_CHECK(cudaEventDestroy(ev));
+    if (computed_entries) *computed_entries = total;
+    return KMG_OK;
 }
 
 int kmg_gram_sharded_takes_host(int n_parts, const int64_t* part_row0, int a, int b, int64_t I, int64_t J) {

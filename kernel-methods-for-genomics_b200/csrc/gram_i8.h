@@ -25,6 +25,7 @@ struct GramI8Args {
     int m_sub;               // 0 = auto, 1 = 128x256 tiles, 2 = 256x256 tiles
     int max_ctas;            // 0 = all SMs
     int64_t* computed_entries;  // optional out: entries actually issued to the tensor cores
+    int mirror_all;          // 1: plain block, but every tile is also stored transposed to out_t[c*ldo_t + r] (block-local r, c)
     // Sharded symmetric build (n_parts > 0): the n x n Gram is cut into n_parts block-rows, one per GPU; this launch
     // computes part `part`'s share of the upper-triangle work and stores every tile twice -- into its own block-row
     // and, transposed, into the block-row of the part that owns the tile's columns (peer device memory).

@@ -93,10 +93,19 @@ def gram_i8(phi_rows, phi_cols, row_index0=0, col_index0=0, out_dtype=KMG_OUT_F6
     return out
 
 
-def gram_i8_sharded(phi, part_row0, part, part_ptrs, ldo, out_dtype=KMG_OUT_F64, sd=None):
+def sharded_stage_bytes(part_row0, part, out_dtype=KMG_OUT_F64):
+    bounds = np.ascontiguousarray(part_row0, np.int64)
+    out = C.c_int64(0)
+    check(_cabi.lib().kmg_gram_sharded_stage_bytes(bounds.size - 1, bounds.ctypes.data_as(C.c_void_p), int(part), out_dtype, C.byref(out)))
+    return out.value
+
+
+def gram_i8_sharded(phi, part_row0, part, part_ptrs, ldo, out_dtype=KMG_OUT_F64, sd=None, stage=None):
     """Part `part`'s launch of the sharded symmetric Gram of all rows of `phi` (kmg_gram_i8_sharded_dev).
     part_row0: len(parts)+1 boundaries; part_ptrs: device address (int) of every part's block-row buffer (row stride ldo
-    elements) -- this device's own allocations or peer memory opened through CUDA IPC.  Returns the entries computed."""
+    elements) -- this device's own allocations or peer memory opened through CUDA IPC.  stage: device address of
+    sharded_stage_bytes() bytes of local staging (one launch + one peer copy per peer block) or None (single launch,
+    epilogue stores into the peers' buffers).  Returns the entries computed."""
     n, W = phi.shape
     g = len(part_ptrs)
     bounds = np.ascontiguousarray(part_row0, np.int64)
@@ -104,7 +113,8 @@ def gram_i8_sharded(phi, part_row0, part, part_ptrs, ldo, out_dtype=KMG_OUT_F64,
     ptrs = (C.c_void_p * g)(*[int(p) for p in part_ptrs])
     computed = C.c_int64(0)
     check(_cabi.lib().kmg_gram_i8_sharded_dev(_p(phi), n, W, phi.stride(0), g, int(part), bounds.ctypes.data_as(C.c_void_p),
-                                              ptrs, int(ldo), out_dtype, _p(sd), C.byref(computed), _stream()))
+                                              ptrs, int(ldo), out_dtype, _p(sd),
+                                              None if stage is None else C.c_void_p(int(stage)), C.byref(computed), _stream()))
     return computed.value
 
 

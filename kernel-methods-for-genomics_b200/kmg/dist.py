@@ -139,8 +139,9 @@ class SymmetricShards:
     """Block-row buffers of one n x n fp64 (or s32) Gram, one per rank of a single node, each visible to every other rank
     through CUDA IPC.  `build_spectrum` fills them with the sharded symmetric GEMM."""
 
-    def __init__(self, n, dtype=torch.float64, group=None):
+    def __init__(self, n, dtype=torch.float64, group=None, staged=True):
         import ctypes as C
+        self.staged = staged
         from . import _cabi
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -167,6 +168,12 @@ class SymmetricShards:
                 self.ptrs[r] = p.value
                 self._opened.append(p)
         self.ptrs[self.rank] = self._own.value
+        # local staging for the transposed blocks that the copy engine ships to their owners
+        from . import device as kd
+        self._stage = C.c_void_p()
+        nbytes = kd.sharded_stage_bytes(self.bounds, self.rank, 1 if esz == 8 else 0)
+        if nbytes:
+            _cabi.check(lib.kmg_dev_malloc(nbytes, C.byref(self._stage)))
         # this rank's block-row as a tensor (no copy): torch reads the CUDA array interface
         holder = type("_Buf", (), {})()
         holder.__cuda_array_interface__ = {"shape": (self.r1 - self.r0, n), "typestr": "<f8" if esz == 8 else "<i4",
@@ -178,7 +185,8 @@ class SymmetricShards:
         """All ranks call this with their local copy of Phi (n x W int8).  Returns entries this rank issued to the MMA."""
         from . import device as kd
         computed = kd.gram_i8_sharded(phi, self.bounds, self.rank, self.ptrs, self.n,
-                                      out_dtype=1 if self.dtype == torch.float64 else 0, sd=sd)
+                                      out_dtype=1 if self.dtype == torch.float64 else 0, sd=sd,
+                                      stage=self._stage.value if (self._stage.value and self.staged) else None)
         return computed
 
     def finish(self):
@@ -200,3 +208,6 @@ class SymmetricShards:
         if self._own is not None and self._own.value:
             lib.kmg_dev_free(self._own)
             self._own = None
+        if self._stage is not None and self._stage.value:
+            lib.kmg_dev_free(self._stage)
+            self._stage = None

@@ -75,16 +75,17 @@ def _nccl_worker(rank, world, port, q):
         full = kdist.gather_rows(blk, n)
         assert torch.equal(full, single)                            # NCCL all-gather materialises it everywhere
         # sharded SYMMETRIC build: half the MMA work per rank, mirror stores into the peers' buffers over CUDA IPC
-        shards = kdist.SymmetricShards(n)
-        for _ in range(2):
-            shards.block.fill_(-1.0)
-            torch.cuda.synchronize()
-            dist.barrier()
-            computed = shards.build_spectrum(phi)
-            shards.finish()
-            assert torch.equal(shards.block, single[shards.r0:shards.r1])
-            assert computed < 0.75 * (shards.r1 - shards.r0) * n
-        shards.close()
+        for staged in (True, False):   # peer copies of staged blocks / epilogue stores straight into peer memory
+            shards = kdist.SymmetricShards(n, staged=staged)
+            for _ in range(2):
+                shards.block.fill_(-1.0)
+                torch.cuda.synchronize()
+                dist.barrier()
+                computed = shards.build_spectrum(phi)
+                shards.finish()
+                assert torch.equal(shards.block, single[shards.r0:shards.r1]), staged
+                assert computed < 0.75 * (shards.r1 - shards.r0) * n
+            shards.close()
         _, _, wblk = kdist.wd_block_row(planes, 101, 10, n)
         wfull = kd.wd_block(planes, planes, 101, 10, symmetric=True)
         cen = kdist.center_block_row(wblk, n)                       # all-reduce of n+1 doubles

@@ -199,16 +199,28 @@ def test_sharded_symmetric_gram_single_device(kd, world):
         if world > 1:
             assert sum(computed) < 0.62 * n * n
             assert all(computed[p] < 0.75 * (bounds[p + 1] - bounds[p]) * n for p in range(world)), computed
+        # staged variant: one launch per peer block into local staging + one pitched copy per block
+        for b in bufs:
+            b.fill_(-7)
+        stages = [torch.empty(max(kd.sharded_stage_bytes(bounds, p, dt), 8), dtype=torch.uint8, device="cuda") for p in range(world)]
+        computed2 = [kd.gram_i8_sharded(phi, bounds, p, ptrs, n, out_dtype=dt, stage=stages[p].data_ptr()) for p in range(world)]
+        torch.cuda.synchronize()
+        assert torch.equal(torch.cat(bufs), ref), (world, ks, dt, "staged")
+        assert computed2 == computed
     # fused cosine normalisation through the mirror stores (kernels.py:398-415)
     phi = kd.spectrum_phi(planes, 101, [4])
     sd = kd.phi_diag_sqrt(phi)
     ref = kd.gram_i8(phi, phi, symmetric=True, sd_rows=sd, sd_cols=sd)
     bounds = kdist.sym_bounds(n, world)
     bufs = [torch.zeros((bounds[p + 1] - bounds[p], n), dtype=torch.float64, device="cuda") for p in range(world)]
-    for p in range(world):
-        kd.gram_i8_sharded(phi, bounds, p, [b.data_ptr() for b in bufs], n, sd=sd)
-    torch.cuda.synchronize()
-    assert torch.equal(torch.cat(bufs), ref)
+    for staged in (False, True):
+        for b in bufs:
+            b.zero_()
+        for p in range(world):
+            st = torch.empty(max(kd.sharded_stage_bytes(bounds, p, 1), 8), dtype=torch.uint8, device="cuda") if staged else None
+            kd.gram_i8_sharded(phi, bounds, p, [b.data_ptr() for b in bufs], n, sd=sd, stage=st.data_ptr() if staged else None)
+            torch.cuda.synchronize()
+        assert torch.equal(torch.cat(bufs), ref), staged
 
 
 def test_full_size_properties(kd):
