@@ -158,11 +158,12 @@ def reference_arm(args, rank):
     print(json.dumps(line), flush=True)
 
 
-def workload_config(n_gpus):
+def workload_config(n_gpus, exchange="n/a (1 GPU)", exchange_checked=None):
     return {"workload": "BASELINE configs[2]: sum of spectrum kernels k=1..7, n=200000 synthetic 101-bp sequences (PCG64 seed 3), "
                         "one 25000 x 200000 fp64 Gram block-row per GPU",
             "n": N_SEQ, "rows_per_gpu": ROWS_PER_GPU, "block_rows_built": n_gpus, "L": L, "ks": KS, "feature_width": D_ALG,
-            "output": "fp64 (exact integers)", "sharding": f"block-row x{n_gpus}, no data-path collective",
+            "output": "fp64 (exact integers)", "sharding": f"block-row x{n_gpus} (boundaries on multiples of 256 rows when N > 1), no collective on the data path",
+            "exchange": exchange, "exchange_checked": exchange_checked,
             "l2": "inputs (Phi 4.4 GB) and output (40 GB) exceed the 126 MB L2; no flush needed"}
 
 
@@ -177,6 +178,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--n", type=int, default=N_SEQ, help="(debug) number of sequences")
     ap.add_argument("--rows", type=int, default=ROWS_PER_GPU, help="(debug) rows per GPU")
+    ap.add_argument("--no-sym", action="store_true", help="N > 1: plain block-rows, no symmetric sharing between the GPUs")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -207,12 +209,53 @@ def main():
     planes = kd.pack(codes, 0)  # every rank holds all packed sequences
     W = kd.phi_width(KS)
     phi = torch.empty((n, W), dtype=torch.int8, device="cuda")
-    row0 = (rank * R) % max(n - R + 1, 1)
-    out = torch.empty((R, n), dtype=torch.float64, device="cuda")
+    # N > 1: the job is rows [0, N*R) of the Gram.  Its leading N*R x N*R square is symmetric, so the ranks share it: each
+    # computes about half of its part of the square and ships the transposed blocks to their owners over NVLink
+    # (kmg/dist.py SymmetricShards: CUDA IPC buffers, one pitched peer copy per block on the copy stream); the columns
+    # [N*R, n) of every block-row are a plain cross-Gram launch.  One all-reduce of a token per step is the barrier that
+    # orders step k+1 after every rank's copies of step k.
+    sym, sym_note, R_tot = None, "n/a (1 GPU)", min(n, world * R)
+    if world > 1 and not args.no_sym:
+        from kmg import dist as kdist
+        try:
+            sym = kdist.SymmetricShards(R_tot, ldo=n)
+            ok, sym_note = 1, "symmetric square shared over NVLink peer memory"
+        except Exception as exc:  # noqa: BLE001 - e.g. CUDA IPC not permitted in this container
+            ok, sym_note = 0, f"plain block-rows ({type(exc).__name__}: {exc})"
+        flag = torch.tensor([ok], dtype=torch.int32, device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            if sym is not None:
+                sym.close()
+            sym, sym_note = None, sym_note if ok == 0 else "plain block-rows (another rank could not map peer memory)"
+    elif world > 1:
+        sym_note = "plain block-rows (--no-sym)"
+    if sym is not None:
+        row0, R, out = sym.r0, sym.r1 - sym.r0, sym.block
+        g = world
+        gemm_launches = 2 * (sum(1 for d in range(1, g) if 2 * d < g) + (1 if g % 2 == 0 else 0)) + 1 + (1 if R_tot < n else 0)  # peer blocks go in two halves
+        token = torch.zeros(1, dtype=torch.int32, device="cuda")
+    else:
+        row0 = (rank * R) % max(n - R + 1, 1)
+        out = torch.empty((R, n), dtype=torch.float64, device="cuda")
+        gemm_launches = 1
+    issued = [0]
+
+    def build():
+        if sym is None:
+            kd.gram_i8(phi[row0:row0 + R], phi, row_index0=row0, col_index0=0, out_dtype=1, m_sub=0, out=out)
+            issued[0] = R * n
+            return
+        issued[0] = sym.build_spectrum(phi[:R_tot])
+        if R_tot < n:
+            kd.gram_i8(phi[row0:row0 + R], phi[R_tot:], row_index0=row0, col_index0=R_tot, out_dtype=1, m_sub=0, out=out[:, R_tot:])
+            issued[0] += R * (n - R_tot)
 
     def step():
         kd.spectrum_phi(planes, L, KS, out=phi)
-        kd.gram_i8(phi[row0:row0 + R], phi, row_index0=row0, col_index0=0, out_dtype=1, m_sub=0, out=out)
+        build()
+        if sym is not None:
+            dist.all_reduce(token)
 
     def barrier():
         if dist is not None:
@@ -231,8 +274,10 @@ def main():
     for i in range(args.steps):
         kd.spectrum_phi(planes, L, KS, out=phi)
         ev[2 * i + 1].record()
-        kd.gram_i8(phi[row0:row0 + R], phi, row_index0=row0, col_index0=0, out_dtype=1, m_sub=0, out=out)
+        build()
         ev[2 * i + 2].record()
+        if sym is not None:
+            dist.all_reduce(token)
     ev[-1].record()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
@@ -243,12 +288,26 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms = float(t.item())
     ms_per_step = total_ms / args.steps
-    entries_per_step = float(R) * n * world
+    entries_per_step = float(R_tot) * n if sym is not None else float(R) * n * world  # Gram entries DELIVERED by all ranks
     value = entries_per_step / (ms_per_step * 1e-3)
+    sym_checked = None
+    if sym is not None:
+        # parity of the shared build: 512 of this rank's rows against a direct launch of the same kernel
+        sym.finish()
+        lo = min(256, max(R - 512, 0))
+        direct = kd.gram_i8(phi[row0 + lo:row0 + lo + 512], phi, row_index0=row0 + lo, col_index0=0, out_dtype=1, m_sub=0)
+        okt = torch.tensor([1 if torch.equal(direct, out[lo:lo + 512]) else 0], dtype=torch.int32, device="cuda")
+        dist.all_reduce(okt, op=dist.ReduceOp.MIN)
+        sym_checked = bool(int(okt.item()))
+        del direct
+        if not sym_checked:
+            raise SystemExit("bench.py: the shared symmetric build disagrees with a direct launch")
 
     # ---- roofline of the dominant kernel (gram_i8_2cta_kernel, the CTA-pair tcgen05 GEMM): tensor bound
     gemm_avg_ms = float(np.mean(gemm_ms))
-    alg_ops = 2.0 * D_ALG * R * n  # 2*D ops per delivered entry, one launch = one block-row
+    # 2*D ops per entry ISSUED to the tensor cores: at N = 1 one launch = one block-row, every entry issued;
+    # in the shared symmetric build a rank issues about half of the entries it ends up holding
+    alg_ops = 2.0 * D_ALG * float(issued[0])
     achieved_tops = alg_ops / (gemm_avg_ms * 1e-3) / 1e12
     peak_tops = 2.0 * peaks["bf16_sustained"]
     roofline = {
@@ -258,8 +317,9 @@ def main():
                        "tcgen05 kind::i8 rate is twice kind::f16; a cuBLAS bf16 denominator doubled, so a tight int8 kernel can read above 1.0",
         "frac_of_nominal_int8_4500": achieved_tops / NOMINAL_INT8_TOPS,
         "algorithmic_ops_per_launch": alg_ops, "kernel_ms": gemm_avg_ms, "kernel_share_of_step": gemm_avg_ms / ms_per_step,
-        "traffic": TRAFFIC_BYTES_PER_LAUNCH,
+        "traffic": TRAFFIC_BYTES_PER_LAUNCH if sym is None else None,
         "hbm_write_gbs": 8.0 * R * n / (gemm_avg_ms * 1e-3) / 1e9,
+        "gemm_launches_per_step": gemm_launches, "entries_issued_over_entries_held": float(issued[0]) / (float(R) * n),
     }
 
     # ---- end to end through the reference-facing C-ABI with host buffers (kmg_spectrum_host)
@@ -298,8 +358,8 @@ def main():
     line = {
         "metric": "gram_entries_per_sec", "value": value, "unit": "entries/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "s8->s32->f64", "data": "synthetic", "config": workload_config(world), "e2e": e2e,
-        "gpu_launches": 2 * args.steps, "roofline": roofline, "clocks": clocks,
+        "dtype": "s8->s32->f64", "data": "synthetic", "config": workload_config(world, sym_note, sym_checked), "e2e": e2e,
+        "gpu_launches": (1 + gemm_launches) * args.steps, "roofline": roofline, "clocks": clocks,
     }
 
     if rank == 0 and world == 1 and not args.no_extras:
@@ -316,6 +376,9 @@ def main():
                                           "dense Phi + dot products as kernels.py:12-47, all host threads)"}
     if rank == 0:
         print(json.dumps(line), flush=True)
+    if sym is not None:
+        out = None
+        sym.close()
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()

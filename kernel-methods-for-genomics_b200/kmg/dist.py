@@ -139,7 +139,9 @@ class SymmetricShards:
     """Block-row buffers of one n x n fp64 (or s32) Gram, one per rank of a single node, each visible to every other rank
     through CUDA IPC.  `build_spectrum` fills them with the sharded symmetric GEMM."""
 
-    def __init__(self, n, dtype=torch.float64, group=None, staged=True):
+    def __init__(self, n, dtype=torch.float64, group=None, staged=True, ldo=None):
+        """n: size of the symmetric square the ranks share; ldo >= n: row stride (and width) of every block-row buffer --
+        columns [n, ldo) are the caller's (e.g. the rest of a wider block-row, filled by a plain cross-Gram launch)."""
         import ctypes as C
         self.staged = staged
         from . import _cabi
@@ -147,12 +149,14 @@ class SymmetricShards:
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.n, self.dtype = n, dtype
+        self.ldo = n if ldo is None else int(ldo)
+        assert self.ldo >= n
         self.bounds = sym_bounds(n, self.world)
         self.r0, self.r1 = self.bounds[self.rank], self.bounds[self.rank + 1]
         esz = 8 if dtype == torch.float64 else 4
         lib = _cabi.lib()
         self._own = C.c_void_p()
-        _cabi.check(lib.kmg_dev_malloc((self.r1 - self.r0) * n * esz, C.byref(self._own)))
+        _cabi.check(lib.kmg_dev_malloc((self.r1 - self.r0) * self.ldo * esz, C.byref(self._own)))
         handle = (C.c_uint8 * 64)()
         self.ptrs = [None] * self.world
         self._opened = []
@@ -176,7 +180,7 @@ class SymmetricShards:
             _cabi.check(lib.kmg_dev_malloc(nbytes, C.byref(self._stage)))
         # this rank's block-row as a tensor (no copy): torch reads the CUDA array interface
         holder = type("_Buf", (), {})()
-        holder.__cuda_array_interface__ = {"shape": (self.r1 - self.r0, n), "typestr": "<f8" if esz == 8 else "<i4",
+        holder.__cuda_array_interface__ = {"shape": (self.r1 - self.r0, self.ldo), "typestr": "<f8" if esz == 8 else "<i4",
                                            "data": (self._own.value, False), "version": 3}
         self._holder = holder
         self.block = torch.as_tensor(holder, device=torch.device("cuda", torch.cuda.current_device()))
@@ -184,7 +188,8 @@ class SymmetricShards:
     def build_spectrum(self, phi, sd=None):
         """All ranks call this with their local copy of Phi (n x W int8).  Returns entries this rank issued to the MMA."""
         from . import device as kd
-        computed = kd.gram_i8_sharded(phi, self.bounds, self.rank, self.ptrs, self.n,
+        assert phi.shape[0] == self.n
+        computed = kd.gram_i8_sharded(phi, self.bounds, self.rank, self.ptrs, self.ldo,
                                       out_dtype=1 if self.dtype == torch.float64 else 0, sd=sd,
                                       stage=self._stage.value if (self._stage.value and self.staged) else None)
         return computed
