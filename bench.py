@@ -233,7 +233,7 @@ def main():
     if sym is not None:
         row0, R, out = sym.r0, sym.r1 - sym.r0, sym.block
         g = world
-        gemm_launches = 2 * (sum(1 for d in range(1, g) if 2 * d < g) + (1 if g % 2 == 0 else 0)) + 1 + (1 if R_tot < n else 0)  # peer blocks go in two halves
+        gemm_launches = sum(1 for d in range(1, g) if 2 * d < g) + (1 if g % 2 == 0 else 0) + 1 + (1 if R_tot < n else 0)
         token = torch.zeros(1, dtype=torch.int32, device="cuda")
     else:
         row0 = (rank * R) % max(n - R + 1, 1)
