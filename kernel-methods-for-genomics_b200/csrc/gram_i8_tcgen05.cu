@@ -696,6 +696,13 @@ int get_tiles(const TileKey& key, cudaStream_t stream, TileList* out) {
     return KMG_OK;
 }
 
+// KMG_GEMM_COOP=0 drops the cooperative attribute: Nsight Compute refuses cooperative cluster launches ("LaunchFailed"),
+// and under the profiler kernels are serialised, so every CTA is resident anyway.  Not for production use.
+bool coop_enabled() {
+    static const int v = env_int("KMG_GEMM_COOP", 1);
+    return v != 0;
+}
+
 template <int M_SUB>
 int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const KernelParams& p, int sms, cudaStream_t stream) {
     using C = Cfg<M_SUB>;
@@ -716,7 +723,7 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const KernelParams& p
     cudaLaunchAttribute attr[1];
     // the wave barrier needs every CTA resident: a cooperative launch makes the driver guarantee it (or fail the launch)
     attr[0].id = cudaLaunchAttributeCooperative;
-    attr[0].val.cooperative = p.wave_counter != nullptr ? 1 : 0;
+    attr[0].val.cooperative = (p.wave_counter != nullptr && coop_enabled()) ? 1 : 0;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     KMG_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gram_i8_tcgen05_kernel<M_SUB>, tmA, tmB, p));
@@ -746,7 +753,7 @@ int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const KernelPara
     attr[0].val.clusterDim.z = 1;
     // the wave barrier needs every CTA resident: a cooperative launch makes the driver guarantee it (or fail the launch)
     attr[1].id = cudaLaunchAttributeCooperative;
-    attr[1].val.cooperative = p.wave_counter != nullptr ? 1 : 0;
+    attr[1].val.cooperative = (p.wave_counter != nullptr && coop_enabled()) ? 1 : 0;
     cfg.attrs = attr;
     cfg.numAttrs = 2;
     KMG_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gram_i8_2cta_kernel<INT_CVT>, tmA, tmB, p));
