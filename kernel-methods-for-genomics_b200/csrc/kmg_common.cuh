@@ -73,6 +73,17 @@ __device__ __forceinline__ void kmg_rotr1_128(uint32_t (&w)[4]) {
     w[3] = __funnelshift_r(w[3], w0, 1);
 }
 
+// rotate right by one inside the low L bits (bits >= L are and stay zero); wrap[] has the single bit L-1 set
+__device__ __forceinline__ void kmg_rotr1_len(uint32_t (&w)[4], const uint32_t (&wrap)[4]) {
+    const uint32_t carry = 0u - (w[0] & 1u);
+    w[0] = __funnelshift_r(w[0], w[1], 1);
+    w[1] = __funnelshift_r(w[1], w[2], 1);
+    w[2] = __funnelshift_r(w[2], w[3], 1);
+    w[3] = w[3] >> 1;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) w[j] |= carry & wrap[j];
+}
+
 // out = in >> S (128-bit logical, compile-time S in [0,127]).
 template <int S>
 __device__ __forceinline__ void kmg_shr_128(const uint32_t (&in)[4], uint32_t (&out)[4]) {

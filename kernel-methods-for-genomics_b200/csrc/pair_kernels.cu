@@ -189,33 +189,40 @@ __device__ __forceinline__ void window_sum_rt(const uint32_t (&e)[4], int k, Cnt
 struct MismatchParams {
     int k;
     int L;
-    int32_t T[8];  // T[delta], zero beyond 2m
+    int32_t T[8];      // T[delta], zero beyond 2m
+    uint32_t wrap[4];  // bit L-1: where bit 0 re-enters when y is rotated inside its L bits
 };
 
-// raw mismatch kernel value of one pair.  vmask[r] = valid window starts for rotation r (shared).
-template <int K, int B>
+// raw mismatch kernel value of one pair.  y is rotated inside its own L bits (not 128): rotation r puts y[(p+r) mod L]
+// under x[p], so one pass serves diagonal +r (windows p <= L-k-r) and diagonal r-L (windows p >= L-r) and L rotations
+// cover all (L-k+1)^2 window pairs -- 101 instead of 128 passes at L = 101.  vmask[r] = valid window starts (shared).
+// NW = words that can hold a window start, ((L-k) >> 5) + 1: the count loop reads only those, and since everything is
+// unrolled straight-line code the compiler drops the upstream shifts / adds of the unused words with them.
+template <int K, int B, int NW>
 __device__ __forceinline__ int64_t mismatch_pair(const SeqPlanes& x, SeqPlanes y, const MismatchParams& mp,
                                                  const uint32_t (*vmask)[4]) {
     constexpr int ND = (1 << B) - 1;  // distances 0..ND-1 are exact, ND-1 >= 2m
     int32_t N[ND];
 #pragma unroll
     for (int d = 0; d < ND; ++d) N[d] = 0;
+    const uint32_t wrap[4] = {mp.wrap[0], mp.wrap[1], mp.wrap[2], mp.wrap[3]};
 #pragma unroll 1
-    for (int r = 0; r < 128; ++r) {
-        const uint32_t v0 = vmask[r][0], v1 = vmask[r][1], v2 = vmask[r][2], v3 = vmask[r][3];
-        if ((v0 | v1 | v2 | v3) != 0u) {  // block-uniform
+    for (int r = 0; r < mp.L; ++r) {
+        uint32_t vm[4];
+#pragma unroll
+        for (int w = 0; w < 4; ++w) vm[w] = w < NW ? vmask[r][w] : 0u;
+        if ((vm[0] | vm[1] | vm[2] | vm[3]) != 0u) {  // block-uniform
             uint32_t e[4];
 #pragma unroll
             for (int w = 0; w < 4; ++w) e[w] = (x.lo[w] ^ y.lo[w]) | (x.hi[w] ^ y.hi[w]);
             Cnt<B> s;
             if (K > 0) window_sum<(K > 0 ? K : 1), B>(e, mp.k, s);
             else window_sum_rt<B>(e, mp.k, s);
-            const uint32_t vm[4] = {v0, v1, v2, v3};
 #pragma unroll
             for (int d = 0; d < ND; ++d) {
                 int cnt = 0;
 #pragma unroll
-                for (int w = 0; w < 4; ++w) {
+                for (int w = 0; w < NW; ++w) {
                     uint32_t eq = vm[w];
 #pragma unroll
                     for (int i = 0; i < B; ++i) eq &= ((d >> i) & 1) ? s.b[i][w] : ~s.b[i][w];
@@ -224,8 +231,8 @@ __device__ __forceinline__ int64_t mismatch_pair(const SeqPlanes& x, SeqPlanes y
                 N[d] += cnt;
             }
         }
-        kmg_rotr1_128(y.lo);
-        kmg_rotr1_128(y.hi);
+        kmg_rotr1_len(y.lo, wrap);
+        kmg_rotr1_len(y.hi, wrap);
     }
     int64_t acc = 0;
 #pragma unroll
@@ -233,19 +240,21 @@ __device__ __forceinline__ int64_t mismatch_pair(const SeqPlanes& x, SeqPlanes y
     return acc;
 }
 
-// valid window-start masks per rotation r: y' = rotr(y, r) puts y[p+r] under x[p] for p+r < 128
-// (diagonal +r) and y[p+r-128] for p+r >= 128 (diagonal r-128).  A window (p, k) is valid iff all
-// its x and y indices are inside [0, L): p in [0, L-k-r] or p in [128-r, L-k].
+// valid window-start masks per rotation r (period L): a window (p, k) under rotation r pairs x[p..p+k) with
+// y[p+r..p+r+k) when p + r + k <= L (diagonal +r: p in [0, L-k-r]) and with y[p+r-L..) when p >= L - r (diagonal r-L:
+// p in [L-r, L-k], non-empty iff r >= k); windows that straddle the wrap point are invalid.
 __device__ __forceinline__ void build_vmask(uint32_t (*vmask)[4], int L, int k) {
     for (int r = threadIdx.x; r < 128; r += blockDim.x) {
         uint32_t m[4] = {0u, 0u, 0u, 0u};
-        if (L - k - r >= 0) kmg_range_mask_128(0, L - k - r, m);
-        if (r >= 1 && 128 - r <= L - k) kmg_range_mask_128(128 - r, L - k, m);
+        if (r < L) {
+            if (L - k - r >= 0) kmg_range_mask_128(0, L - k - r, m);
+            if (r >= 1 && r >= k) kmg_range_mask_128(L - r, L - k, m);
+        }
         vmask[r][0] = m[0]; vmask[r][1] = m[1]; vmask[r][2] = m[2]; vmask[r][3] = m[3];
     }
 }
 
-template <int K, int B>
+template <int K, int B, int NW>
 __global__ void __launch_bounds__(TILE_R * TILE_C)
 mismatch_kernel(const uint32_t* __restrict__ prow, const uint32_t* __restrict__ pcol, const OutSpec o,
                 const MismatchParams mp) {
@@ -259,11 +268,11 @@ mismatch_kernel(const uint32_t* __restrict__ prow, const uint32_t* __restrict__ 
     const bool live = r < o.rows && c < o.cols;
     const SeqPlanes x = kmg_load_planes(prow, live ? r : 0);
     const SeqPlanes y = kmg_load_planes(pcol, live ? c : 0);
-    const int64_t raw = mismatch_pair<K, B>(x, y, mp, vmask);
+    const int64_t raw = mismatch_pair<K, B, NW>(x, y, mp, vmask);
     if (live) store_int(o, r, c, raw, cls == 1);
 }
 
-template <int K, int B>
+template <int K, int B, int NW>
 __global__ void __launch_bounds__(256)
 mismatch_diag_kernel(const uint32_t* __restrict__ planes, int64_t n, const MismatchParams mp, double* __restrict__ sd) {
     __shared__ uint32_t vmask[128][4];
@@ -271,7 +280,7 @@ mismatch_diag_kernel(const uint32_t* __restrict__ planes, int64_t n, const Misma
     __syncthreads();
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     const SeqPlanes x = kmg_load_planes(planes, i < n ? i : 0);
-    const int64_t raw = mismatch_pair<K, B>(x, x, mp, vmask);
+    const int64_t raw = mismatch_pair<K, B, NW>(x, x, mp, vmask);
     if (i < n) sd[i] = sqrt((double)raw);  // np.sqrt(np.diag(K)), kernels.py:408 (IEEE, correctly rounded)
 }
 
@@ -463,33 +472,36 @@ int check_block(const PairBlock* b) {
     return KMG_OK;
 }
 
-template <int B>
+// words that can hold a window start: 3 when L - k + 1 <= 96 (the 101-bp data of the reference at every k >= 6), else 4
+inline int mm_result_words(const MismatchParams& mp) { return ((mp.L - mp.k) >> 5) + 1 <= 3 ? 3 : 4; }
+
+template <int B, int NW>
 int launch_mismatch_k(const PairBlock* b, const OutSpec& o, const MismatchParams& mp, cudaStream_t stream) {
     dim3 grid((unsigned)((b->cols + TILE_C - 1) / TILE_C), (unsigned)((b->rows + TILE_R - 1) / TILE_R));
     dim3 block(TILE_R * TILE_C);
 #define KMG_MM_CASE(KK) \
-    case KK: mismatch_kernel<KK, B><<<grid, block, 0, stream>>>(b->planes_rows, b->planes_cols, o, mp); break;
+    case KK: mismatch_kernel<KK, B, NW><<<grid, block, 0, stream>>>(b->planes_rows, b->planes_cols, o, mp); break;
     switch (mp.k) {
         KMG_MM_CASE(1) KMG_MM_CASE(2) KMG_MM_CASE(3) KMG_MM_CASE(4) KMG_MM_CASE(5) KMG_MM_CASE(6) KMG_MM_CASE(7)
         KMG_MM_CASE(8) KMG_MM_CASE(9) KMG_MM_CASE(10) KMG_MM_CASE(11) KMG_MM_CASE(12) KMG_MM_CASE(13) KMG_MM_CASE(14)
         KMG_MM_CASE(15) KMG_MM_CASE(16)
-        default: mismatch_kernel<0, B><<<grid, block, 0, stream>>>(b->planes_rows, b->planes_cols, o, mp); break;
+        default: mismatch_kernel<0, B, NW><<<grid, block, 0, stream>>>(b->planes_rows, b->planes_cols, o, mp); break;
     }
 #undef KMG_MM_CASE
     KMG_CUDA_CHECK(cudaGetLastError());
     return KMG_OK;
 }
 
-template <int B>
+template <int B, int NW>
 int launch_mismatch_diag_k(const uint32_t* planes, int64_t n, const MismatchParams& mp, double* sd, cudaStream_t stream) {
     const unsigned grid = (unsigned)((n + 255) / 256);
 #define KMG_MM_CASE(KK) \
-    case KK: mismatch_diag_kernel<KK, B><<<grid, 256, 0, stream>>>(planes, n, mp, sd); break;
+    case KK: mismatch_diag_kernel<KK, B, NW><<<grid, 256, 0, stream>>>(planes, n, mp, sd); break;
     switch (mp.k) {
         KMG_MM_CASE(1) KMG_MM_CASE(2) KMG_MM_CASE(3) KMG_MM_CASE(4) KMG_MM_CASE(5) KMG_MM_CASE(6) KMG_MM_CASE(7)
         KMG_MM_CASE(8) KMG_MM_CASE(9) KMG_MM_CASE(10) KMG_MM_CASE(11) KMG_MM_CASE(12) KMG_MM_CASE(13) KMG_MM_CASE(14)
         KMG_MM_CASE(15) KMG_MM_CASE(16)
-        default: mismatch_diag_kernel<0, B><<<grid, 256, 0, stream>>>(planes, n, mp, sd); break;
+        default: mismatch_diag_kernel<0, B, NW><<<grid, 256, 0, stream>>>(planes, n, mp, sd); break;
     }
 #undef KMG_MM_CASE
     KMG_CUDA_CHECK(cudaGetLastError());
@@ -507,6 +519,7 @@ int fill_mismatch_params(int k, int m, int L, MismatchParams* mp, int* bits) {
         KMG_REQUIRE(T[d] < (1ll << 31), KMG_ERR_UNSUPPORTED, "mismatch: neighbourhood table overflows int32");
         mp->T[d] = (int32_t)T[d];
     }
+    for (int w = 0; w < 4; ++w) mp->wrap[w] = (w == ((L - 1) >> 5)) ? (1u << ((L - 1) & 31)) : 0u;
     *bits = (m == 0) ? 1 : (m == 1 ? 2 : 3);
     return KMG_OK;
 }
@@ -550,9 +563,14 @@ int kmg_mismatch_launch(const PairBlock* b, int k, int m, cudaStream_t stream) {
                 "mismatch: raw values may overflow int32, use the f64 output");
     if (b->rows == 0 || b->cols == 0) return KMG_OK;
     const OutSpec o = make_out(b);
-    if (bits == 1) return launch_mismatch_k<1>(b, o, mp, stream);
-    if (bits == 2) return launch_mismatch_k<2>(b, o, mp, stream);
-    return launch_mismatch_k<3>(b, o, mp, stream);
+    if (mm_result_words(mp) == 3) {
+        if (bits == 1) return launch_mismatch_k<1, 3>(b, o, mp, stream);
+        if (bits == 2) return launch_mismatch_k<2, 3>(b, o, mp, stream);
+        return launch_mismatch_k<3, 3>(b, o, mp, stream);
+    }
+    if (bits == 1) return launch_mismatch_k<1, 4>(b, o, mp, stream);
+    if (bits == 2) return launch_mismatch_k<2, 4>(b, o, mp, stream);
+    return launch_mismatch_k<3, 4>(b, o, mp, stream);
 }
 
 int kmg_mismatch_diag_launch(const uint32_t* planes, int64_t n, int L, int k, int m, double* sd, cudaStream_t stream) {
@@ -562,9 +580,14 @@ int kmg_mismatch_diag_launch(const uint32_t* planes, int64_t n, int L, int k, in
     int rc = fill_mismatch_params(k, m, L, &mp, &bits);
     if (rc) return rc;
     if (n <= 0) return KMG_OK;
-    if (bits == 1) return launch_mismatch_diag_k<1>(planes, n, mp, sd, stream);
-    if (bits == 2) return launch_mismatch_diag_k<2>(planes, n, mp, sd, stream);
-    return launch_mismatch_diag_k<3>(planes, n, mp, sd, stream);
+    if (mm_result_words(mp) == 3) {
+        if (bits == 1) return launch_mismatch_diag_k<1, 3>(planes, n, mp, sd, stream);
+        if (bits == 2) return launch_mismatch_diag_k<2, 3>(planes, n, mp, sd, stream);
+        return launch_mismatch_diag_k<3, 3>(planes, n, mp, sd, stream);
+    }
+    if (bits == 1) return launch_mismatch_diag_k<1, 4>(planes, n, mp, sd, stream);
+    if (bits == 2) return launch_mismatch_diag_k<2, 4>(planes, n, mp, sd, stream);
+    return launch_mismatch_diag_k<3, 4>(planes, n, mp, sd, stream);
 }
 
 int kmg_wd_launch(const PairBlock* b, int d, cudaStream_t stream) {

@@ -99,7 +99,8 @@ def test_mismatch_pairwise_raw_vs_oracle(kd, kh, dna):
     assert np.array_equal(blk, want[33:77])
     assert np.array_equal(kh.mismatch_gram(c[:10], 10, 1, cols=c[50:90], normalize=False), raw[:10, 50:90])
     # other lengths
-    for L, k, m in ((12, 5, 1), (64, 9, 2), (128, 11, 1), (128, 8, 1)):
+    for L, k, m in ((12, 5, 1), (64, 9, 2), (128, 11, 1), (128, 8, 1), (1, 1, 0), (33, 1, 0), (97, 2, 1), (100, 4, 1), (100, 5, 2),
+                    (128, 128, 1), (96, 1, 1), (127, 32, 3)):
         cc = onp.synthetic_codes(40, L, seed=L + k)
         got = kh.mismatch_gram(cc, k, m, normalize=False, algo=1)
         assert np.array_equal(got, oc.mismatch_raw_block(cc, cc, k, m).astype(np.float64)), (L, k, m)
