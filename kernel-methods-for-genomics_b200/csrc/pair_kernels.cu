@@ -301,6 +301,40 @@ struct WdParams {
 constexpr int WD_PPT = 4;
 constexpr int WD_TILE_C = TILE_C * WD_PPT;
 
+// One k of the weighted-degree sum for the WD_PPT pairs of a thread: m &= (match >> (k-1)), c_k = popc(m),
+// acc += beta_k * c_k (kernels.py:74-80).  NW = words of the 128-bit vectors that can still be non-zero.
+// Returns true when no pair of the warp has a run of length k left (the remaining terms add +0.0).
+template <int NW>
+__device__ __forceinline__ bool wd_step(uint32_t (&m)[WD_PPT][4], uint32_t (&sh)[WD_PPT][4], double (&acc)[WD_PPT], int k, double bk) {
+    uint32_t any = 0u;
+#pragma unroll
+    for (int j = 0; j < WD_PPT; ++j) {
+        if (k > 1) {
+#pragma unroll
+            for (int w = 0; w < NW; ++w) {
+                const uint32_t hi = (w + 1 < NW) ? sh[j][w + 1 < 4 ? w + 1 : 3] : 0u;  // words >= NW are zero by now
+                sh[j][w] = __funnelshift_r(sh[j][w], hi, 1);
+                m[j][w] &= sh[j][w];
+            }
+        }
+#pragma unroll
+        for (int w = 0; w < NW; ++w) any |= m[j][w];
+    }
+    if (__all_sync(0xffffffffu, any == 0u)) return true;
+#pragma unroll
+    for (int j = 0; j < WD_PPT; ++j) {
+        // The XU pipe (POPC, I2F) is the busiest one (ncu 65 %): a carry-save adder over three of the four words
+        // trades one POPC for two LOP3, and the exact int -> double conversion is one FP64 add of 2^52.
+        const uint32_t s3 = m[j][0] ^ m[j][1] ^ m[j][2];
+        const uint32_t cy = (m[j][0] & m[j][1]) | (m[j][2] & (m[j][0] ^ m[j][1]));
+        int cnt = __popc(s3) + 2 * __popc(cy);
+        if (NW == 4) cnt += __popc(m[j][3]);
+        const double cd = __hiloint2double(0x43300000, cnt) - 4503599627370496.0;
+        acc[j] = __dadd_rn(acc[j], __dmul_rn(bk, cd));
+    }
+    return false;
+}
+
 __global__ void __launch_bounds__(TILE_R * TILE_C)
 wd_kernel(const uint32_t* __restrict__ prow, const uint32_t* __restrict__ pcol, const OutSpec o, const WdParams wp) {
     __shared__ double tile[TILE_R][WD_TILE_C + 1];
@@ -330,30 +364,19 @@ wd_kernel(const uint32_t* __restrict__ prow, const uint32_t* __restrict__ pcol, 
     double acc[WD_PPT];
 #pragma unroll
     for (int j = 0; j < WD_PPT; ++j) acc[j] = 0.0;
+    // The shifted match vector of iteration k is match >> (k-1), bits <= L - k: after the iteration k = L - 95 its fourth
+    // word is empty (and so is the run vector's), so the later iterations work on three words (L = 101: k >= 7, a
+    // quarter of the shift / and / popc work of those iterations).
+    const int k4 = min(wp.d, wp.L - 95);  // last k done on all four words (<= 0: none)
+    bool done = false;
 #pragma unroll 1
-    for (int k = 1; k <= wp.d; ++k) {
-        uint32_t any = 0u;
-#pragma unroll
-        for (int j = 0; j < WD_PPT; ++j) {
-            if (k > 1) {
-                kmg_shr1_128(sh[j]);
-#pragma unroll
-                for (int w = 0; w < 4; ++w) m[j][w] &= sh[j][w];
-            }
-            any |= m[j][0] | m[j][1] | m[j][2] | m[j][3];
-        }
-        // none of the 128 pairs of this warp has a run of length k left: the remaining terms add +0.0
-        if (__all_sync(0xffffffffu, any == 0u)) break;
-        const double bk = wp.beta[k - 1];
-#pragma unroll
-        for (int j = 0; j < WD_PPT; ++j) {
-            // The XU pipe (POPC, I2F) is the busiest one (ncu 65 %): a carry-save adder over three of the four words
-            // trades one POPC for two LOP3, and the exact int -> double conversion is one FP64 add of 2^52.
-            const uint32_t s3 = m[j][0] ^ m[j][1] ^ m[j][2];
-            const uint32_t cy = (m[j][0] & m[j][1]) | (m[j][2] & (m[j][0] ^ m[j][1]));
-            const int cnt = __popc(s3) + 2 * __popc(cy) + __popc(m[j][3]);
-            const double cd = __hiloint2double(0x43300000, cnt) - 4503599627370496.0;
-            acc[j] = __dadd_rn(acc[j], __dmul_rn(bk, cd));
+    for (int k = 1; k <= k4; ++k) {
+        if (wd_step<4>(m, sh, acc, k, wp.beta[k - 1])) { done = true; break; }
+    }
+    if (!done) {
+#pragma unroll 1
+        for (int k = max(k4, 0) + 1; k <= wp.d; ++k) {
+            if (wd_step<3>(m, sh, acc, k, wp.beta[k - 1])) break;
         }
     }
 #pragma unroll

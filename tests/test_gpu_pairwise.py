@@ -63,6 +63,15 @@ def test_wd_blocks_and_edges(kd, kh, dna):
     for L, d in ((2, 1), (33, 40), (64, 3), (128, 20)):
         cc = onp.synthetic_codes(70, L, seed=L)
         assert np.array_equal(kh.wd_gram(cc, d), oc.wd_block(cc, cc, d)), (L, d)
+    # long runs (near-duplicates) around the 96-bit boundary where the kernel drops to three words per vector
+    rng = np.random.default_rng(7)
+    for L, d in ((95, 10), (96, 10), (97, 12), (100, 30), (101, 10), (101, 60), (101, 101), (128, 127), (128, 33)):
+        base = onp.synthetic_codes(6, L, seed=100 + L)
+        cc = np.repeat(base, 8, axis=0)
+        hit = rng.random(cc.shape) < 0.03
+        cc = np.where(hit, (cc + rng.integers(1, 4, cc.shape)) % 4, cc).astype(np.uint8)
+        assert np.array_equal(kh.wd_gram(cc, d), oc.wd_block(cc, cc, d)), (L, d)
+        assert np.array_equal(kh.wd_gram(cc[:7], d, cols=cc[5:]), oc.wd_block(cc[:7], cc[5:], d, 0, 1 << 40)), (L, d)
     assert kh.wd_gram(codes[:0], 3).shape == (0, 0)
     assert np.array_equal(kh.wd_gram(codes[:9], 5, cols=codes[20:51]), oc.wd_block(codes[:9], codes[20:51], 5, 0, 1 << 40))
 
