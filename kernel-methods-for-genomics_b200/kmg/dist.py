@@ -155,29 +155,48 @@ class SymmetricShards:
         self.r0, self.r1 = self.bounds[self.rank], self.bounds[self.rank + 1]
         esz = 8 if dtype == torch.float64 else 4
         lib = _cabi.lib()
-        self._own = C.c_void_p()
-        _cabi.check(lib.kmg_dev_malloc((self.r1 - self.r0) * self.ldo * esz, C.byref(self._own)))
-        handle = (C.c_uint8 * 64)()
+        from . import device as kd
+        self._own, self._stage = C.c_void_p(), C.c_void_p()
         self.ptrs = [None] * self.world
         self._opened = []
+        # Every step that can fail (allocation, IPC export / open) is followed by an exchange of the outcome, so a rank
+        # that fails never leaves the others waiting inside a collective: all ranks raise together.
+        payload, err = None, None
+        try:
+            _cabi.check(lib.kmg_dev_malloc((self.r1 - self.r0) * self.ldo * esz, C.byref(self._own)))
+            nbytes = kd.sharded_stage_bytes(self.bounds, self.rank, 1 if esz == 8 else 0)
+            if nbytes:  # local staging for the transposed blocks that the copy engine ships to their owners
+                _cabi.check(lib.kmg_dev_malloc(nbytes, C.byref(self._stage)))
+            if self.world > 1:
+                handle = (C.c_uint8 * 64)()
+                _cabi.check(lib.kmg_ipc_export(self._own, handle))
+                payload = bytes(handle)
+        except Exception as exc:  # noqa: BLE001
+            err = exc
         if self.world > 1:
-            _cabi.check(lib.kmg_ipc_export(self._own, handle))
             handles = [None] * self.world
-            dist.all_gather_object(handles, bytes(handle), group=group)
-            for r, h in enumerate(handles):
-                if r == self.rank:
-                    continue
-                p = C.c_void_p()
-                _cabi.check(lib.kmg_ipc_open((C.c_uint8 * 64).from_buffer_copy(h), C.byref(p)))
-                self.ptrs[r] = p.value
-                self._opened.append(p)
+            dist.all_gather_object(handles, payload, group=group)
+            if err is None and all(h is not None for h in handles):
+                try:
+                    for r, h in enumerate(handles):
+                        if r == self.rank:
+                            continue
+                        p = C.c_void_p()
+                        _cabi.check(lib.kmg_ipc_open((C.c_uint8 * 64).from_buffer_copy(h), C.byref(p)))
+                        self.ptrs[r] = p.value
+                        self._opened.append(p)
+                except Exception as exc:  # noqa: BLE001
+                    err = exc
+            elif err is None:
+                err = RuntimeError("another rank could not allocate or export its block-row buffer")
+            oks = [None] * self.world
+            dist.all_gather_object(oks, err is None, group=group)
+            if err is None and not all(oks):
+                err = RuntimeError("another rank could not map the peer buffers")
+        if err is not None:
+            self._release()
+            raise err
         self.ptrs[self.rank] = self._own.value
-        # local staging for the transposed blocks that the copy engine ships to their owners
-        from . import device as kd
-        self._stage = C.c_void_p()
-        nbytes = kd.sharded_stage_bytes(self.bounds, self.rank, 1 if esz == 8 else 0)
-        if nbytes:
-            _cabi.check(lib.kmg_dev_malloc(nbytes, C.byref(self._stage)))
         # this rank's block-row as a tensor (no copy): torch reads the CUDA array interface
         holder = type("_Buf", (), {})()
         holder.__cuda_array_interface__ = {"shape": (self.r1 - self.r0, self.ldo), "typestr": "<f8" if esz == 8 else "<i4",
@@ -200,19 +219,21 @@ class SymmetricShards:
         if self.world > 1:
             dist.barrier(group=self.group)
 
-    def close(self):
+    def _release(self):
         from . import _cabi
         lib = _cabi.lib()
+        for p in self._opened:
+            lib.kmg_ipc_close(p)
+        self._opened = []
+        for name in ("_own", "_stage"):
+            p = getattr(self, name, None)
+            if p is not None and p.value:
+                lib.kmg_dev_free(p)
+            setattr(self, name, None)
+
+    def close(self):
         self.block = None
         if self.world > 1:
             torch.cuda.synchronize()
             dist.barrier(group=self.group)  # nobody still writes into a buffer that is about to be unmapped
-        for p in self._opened:
-            lib.kmg_ipc_close(p)
-        self._opened = []
-        if self._own is not None and self._own.value:
-            lib.kmg_dev_free(self._own)
-            self._own = None
-        if self._stage is not None and self._stage.value:
-            lib.kmg_dev_free(self._stage)
-            self._stage = None
+        self._release()

@@ -53,6 +53,16 @@ def _worker(rank, world, port, n, q):
         # --- sharded Frobenius product (exact: integer-valued Grams)
         fro = kdist.frobenius_sharded(blk, blk, lambda a, b: (a * b).sum())
         assert float(fro) == float((full * full).sum())
+        # --- the shared symmetric build has no CPU path: without a GPU every rank must raise together (the failure is
+        # exchanged before anyone enters the next collective), none may hang
+        from kmg._cabi import KmgError
+        if not torch.cuda.is_available():
+            try:
+                kdist.SymmetricShards(256 * world)
+                raise AssertionError("SymmetricShards must not succeed without a CUDA device")
+            except (KmgError, RuntimeError) as exc:
+                assert "no CPU fallback" in str(exc) or "another rank" in str(exc), str(exc)
+            dist.barrier()
         q.put((rank, "ok"))
     except Exception as e:  # pragma: no cover - reported to the parent
         import traceback
