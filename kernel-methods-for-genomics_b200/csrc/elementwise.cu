@@ -17,6 +17,8 @@
 
 namespace {
 
+constexpr int EW_PER_THREAD = 4;  // elements per thread of the row-wise passes (memory-level parallelism)
+
 __global__ void diag_sqrt_kernel(const double* __restrict__ K, int64_t n, int64_t ld, double* __restrict__ sd) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i < n) sd[i] = sqrt(K[i * ld + i]);  // np.sqrt(np.diag(K)), kernels.py:408
@@ -26,7 +28,7 @@ __global__ void diag_sqrt_kernel(const double* __restrict__ K, int64_t n, int64_
 // (i,j) and -- through a shared-memory transpose -- to (j,i), exactly the mirror of kernels.py:412-413.
 __global__ void __launch_bounds__(256) normalize_kernel(double* __restrict__ K, int64_t n, int64_t ld, const double* __restrict__ sd) {
     const int64_t bi = blockIdx.y, bj = blockIdx.x;
-    if (bj < bi) return;
+    if (bj < bi) return;  // (enumerating only the upper-triangle tile pairs was measured: no faster)
     __shared__ double tile[32][33];
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
 #pragma unroll
@@ -113,11 +115,24 @@ __global__ void __launch_bounds__(256) vec_sum_kernel(const double* __restrict__
 __global__ void __launch_bounds__(256) center_apply_kernel(const double* __restrict__ K, int64_t cols, int64_t n, int64_t ld,
                                                            const double* __restrict__ rs, const double* __restrict__ cs,
                                                            const double* __restrict__ g, double* __restrict__ out, int64_t ldo) {
-    const int64_t j = blockIdx.x * 256ll + threadIdx.x;
+    // four columns per thread, 256 apart: four independent 8-byte loads in flight per thread (one per thread left the
+    // pass at 4.4 TB/s, latency bound: 16 KB in flight per SM against the ~35 KB that 6.5 TB/s needs)
+    const int64_t j0 = blockIdx.x * (256ll * EW_PER_THREAD) + threadIdx.x;
     const int64_t i = blockIdx.y;
-    if (j >= cols) return;
     const double inv = 1.0 / (double)n;
-    out[i * ldo + j] = K[i * ld + j] - cs[j] * inv - rs[i] * inv + (*g) * inv * inv;
+    const double ri = rs[i] * inv, gg = (*g) * inv * inv;
+    double v[EW_PER_THREAD], c[EW_PER_THREAD];
+#pragma unroll
+    for (int q = 0; q < EW_PER_THREAD; ++q) {
+        const int64_t j = j0 + 256 * q;
+        v[q] = j < cols ? K[i * ld + j] : 0.0;
+        c[q] = j < cols ? cs[j] : 0.0;
+    }
+#pragma unroll
+    for (int q = 0; q < EW_PER_THREAD; ++q) {
+        const int64_t j = j0 + 256 * q;
+        if (j < cols) out[i * ldo + j] = v[q] - c[q] * inv - ri + gg;
+    }
 }
 
 __global__ void __launch_bounds__(256) gather_kernel(const double* __restrict__ K, int64_t ld, const int64_t* __restrict__ idx,
@@ -139,16 +154,32 @@ struct CombineParams {
 // out = (sum_m u_m K_m) ** degree, products and sums rounded separately in the order numpy uses
 // (np.sum(kernels * u[:,None,None], axis=0): K_0 u_0, then + K_1 u_1, ...).
 __global__ void __launch_bounds__(256) combine_kernel(CombineParams cp, int64_t rows, int64_t cols, double* __restrict__ out, int64_t ldo) {
-    const int64_t j = blockIdx.x * 256ll + threadIdx.x;
+    const int64_t j0 = blockIdx.x * (256ll * EW_PER_THREAD) + threadIdx.x;
     const int64_t i = blockIdx.y;
-    if (j >= cols || i >= rows) return;
-    double acc = __dmul_rn(cp.K[0][i * cp.ld[0] + j], cp.u[0]);
-    for (int m = 1; m < cp.p; ++m) acc = __dadd_rn(acc, __dmul_rn(cp.K[m][i * cp.ld[m] + j], cp.u[m]));
-    double v = acc;
-    if (cp.degree == 0) v = 1.0;
-    else if (cp.degree == 2) v = __dmul_rn(acc, acc);  // numpy: x**2 -> np.square
-    else if (cp.degree != 1) v = pow(acc, (double)cp.degree);
-    out[i * ldo + j] = v;
+    if (i >= rows) return;
+    double acc[EW_PER_THREAD];
+#pragma unroll
+    for (int q = 0; q < EW_PER_THREAD; ++q) {
+        const int64_t j = j0 + 256 * q;
+        acc[q] = j < cols ? __dmul_rn(cp.K[0][i * cp.ld[0] + j], cp.u[0]) : 0.0;
+    }
+    for (int m = 1; m < cp.p; ++m) {
+#pragma unroll
+        for (int q = 0; q < EW_PER_THREAD; ++q) {
+            const int64_t j = j0 + 256 * q;
+            if (j < cols) acc[q] = __dadd_rn(acc[q], __dmul_rn(cp.K[m][i * cp.ld[m] + j], cp.u[m]));
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < EW_PER_THREAD; ++q) {
+        const int64_t j = j0 + 256 * q;
+        if (j >= cols) continue;
+        double v = acc[q];
+        if (cp.degree == 0) v = 1.0;
+        else if (cp.degree == 2) v = __dmul_rn(acc[q], acc[q]);  // numpy: x**2 -> np.square
+        else if (cp.degree != 1) v = pow(acc[q], (double)cp.degree);
+        out[i * ldo + j] = v;
+    }
 }
 
 // partial[b] = sum over the block's elements of A_ij * (B ? B_ij : 1) * (w ? w_i w_j : 1)
@@ -233,7 +264,7 @@ int kmg_ew_center(const double* K, int64_t n, int64_t ld, double* out, int64_t l
     col_sum_partial_kernel<<<dim3((unsigned)((n + 255) / 256), (unsigned)chunks), 256, 0, s>>>(K, n, n, ld, part);
     col_sum_final_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(part, chunks, n, cs);
     vec_sum_kernel<<<1, 256, 0, s>>>(rs, n, g);
-    center_apply_kernel<<<dim3((unsigned)((n + 255) / 256), (unsigned)n), 256, 0, s>>>(K, n, n, ld, rs, cs, g, out, ldo);
+    center_apply_kernel<<<dim3((unsigned)((n + 256 * EW_PER_THREAD - 1) / (256 * EW_PER_THREAD)), (unsigned)n), 256, 0, s>>>(K, n, n, ld, rs, cs, g, out, ldo);
     KMG_CUDA_CHECK(cudaGetLastError());
     return KMG_OK;
 }
@@ -255,7 +286,7 @@ int kmg_ew_combine(const double* const* Ks, const int64_t* lds, const double* u,
     CombineParams cp;
     cp.p = p; cp.degree = degree;
     for (int m = 0; m < p; ++m) { cp.K[m] = Ks[m]; cp.ld[m] = lds[m]; cp.u[m] = u[m]; }
-    combine_kernel<<<dim3((unsigned)((cols + 255) / 256), (unsigned)rows), 256, 0, s>>>(cp, rows, cols, out, ldo);
+    combine_kernel<<<dim3((unsigned)((cols + 256 * EW_PER_THREAD - 1) / (256 * EW_PER_THREAD)), (unsigned)rows), 256, 0, s>>>(cp, rows, cols, out, ldo);
     KMG_CUDA_CHECK(cudaGetLastError());
     return KMG_OK;
 }
@@ -297,7 +328,7 @@ int kmg_ew_center_apply(const double* K, int64_t rows, int64_t cols, int64_t n_t
                         const double* g, double* out, int64_t ldo, cudaStream_t s) {
     if (rows <= 0 || cols <= 0) return KMG_OK;
     KMG_REQUIRE(rows <= 65535, KMG_ERR_ARG, "center_apply: too many rows for one launch");
-    center_apply_kernel<<<dim3((unsigned)((cols + 255) / 256), (unsigned)rows), 256, 0, s>>>(K, cols, n_total, ld, rs, cs, g, out, ldo);
+    center_apply_kernel<<<dim3((unsigned)((cols + 256 * EW_PER_THREAD - 1) / (256 * EW_PER_THREAD)), (unsigned)rows), 256, 0, s>>>(K, cols, n_total, ld, rs, cs, g, out, ldo);
     KMG_CUDA_CHECK(cudaGetLastError());
     return KMG_OK;
 }

@@ -68,6 +68,20 @@ def main():
                 out = torch.empty((n, n), dtype=torch.float64, device="cuda")
                 med, best = timeit(lambda: kd.gram_i8(phi[:n], phi[:n], out_dtype=1, symmetric=True, out=out))
                 print(f"gemm ks={ks[0]}..{ks[-1]} W={W} {n}x{n} symmetric f64: {med:.3f} ms  {n * n / med / 1e6:.2f} Gentries/s delivered")
+    if "ew" in what:
+        # stored-Gram passes (HBM bound): bytes = reads + writes of the pass
+        m = min(n, 16384)
+        Ks = [torch.rand((m, m), dtype=torch.float64, device="cuda") + 1.0 for _ in range(3)]
+        u = [0.2, 0.3, 0.5]
+        for name, fn, nbytes in (
+                ("center (row sums + col sums + apply)", lambda: kd.center(Ks[0]), 8.0 * m * m * 4),
+                ("combine p=3 degree 2", lambda: kd.combine(Ks, u, 2), 8.0 * m * m * 4),
+                ("combine p=1 degree 1", lambda: kd.combine(Ks[:1], u[:1], 1), 8.0 * m * m * 2),
+                ("normalize (in place)", lambda: kd.normalize_(Ks[1]), 8.0 * m * m * 1.5),
+                ("row_sums", lambda: kd.row_sums(Ks[2]), 8.0 * m * m),
+                ("weighted_dot <A,B>", lambda: kd.weighted_dot(Ks[0], Ks[2]), 8.0 * m * m * 2)):
+            med, best = timeit(fn)
+            print(f"ew {name} {m}x{m}: {med:.3f} ms  {nbytes / med / 1e6:.0f} GB/s")
     if "cublas" in what:
         # library reference for context only (cuBLASLt int8 IMMA through torch._int_mm, s32 output): not a product path
         for W in (4096, 21888):
