@@ -2,9 +2,9 @@
 import os, sys, time
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path.insert(0, os.path.join(ROOT, "kernel-methods-for-genomics_b200")); sys.path.insert(0, os.path.join(ROOT, "oracle"))
+sys.path.insert(0, os.path.join(ROOT, "kernel-methods-for-genomics_b200")); sys.path.insert(0, os.path.join(ROOT, "tools"))
 from kmg import host as kh
-import oracle_np as onp
+import _inputs as onp
 n = 200000
 codes = onp.synthetic_codes(n, 101, seed=3)
 rows = np.ascontiguousarray(codes[:2048])

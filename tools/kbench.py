@@ -8,11 +8,11 @@ import numpy as np
 import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-for p in (os.path.join(ROOT, "kernel-methods-for-genomics_b200"), os.path.join(ROOT, "oracle")):
+for p in (os.path.join(ROOT, "kernel-methods-for-genomics_b200"), os.path.join(ROOT, "tools")):
     sys.path.insert(0, p)
 
 from kmg import device as kd  # noqa: E402
-import oracle_np as onp  # noqa: E402
+import _inputs as onp  # noqa: E402
 
 
 def timeit(fn, warmup=2, iters=5):

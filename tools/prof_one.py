@@ -2,10 +2,10 @@
 import argparse, os, sys
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-for p in (os.path.join(ROOT, "kernel-methods-for-genomics_b200"), os.path.join(ROOT, "oracle")):
+for p in (os.path.join(ROOT, "kernel-methods-for-genomics_b200"), os.path.join(ROOT, "tools")):
     sys.path.insert(0, p)
 from kmg import device as kd
-import oracle_np as onp
+import _inputs as onp
 ap = argparse.ArgumentParser()
 ap.add_argument("--kind", default="gemm")
 ap.add_argument("--rows", type=int, default=16384)

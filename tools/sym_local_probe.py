@@ -3,11 +3,11 @@ the tile assignment / mirror stores from the cost of storing into peer memory.""
 import os, sys
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-for p in (os.path.join(ROOT, "kernel-methods-for-genomics_b200"), os.path.join(ROOT, "oracle")):
+for p in (os.path.join(ROOT, "kernel-methods-for-genomics_b200"), os.path.join(ROOT, "tools")):
     sys.path.insert(0, p)
 from kmg import device as kd
 from kmg import dist as kdist
-import oracle_np as onp
+import _inputs as onp
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 100000
 world = int(sys.argv[2]) if len(sys.argv) > 2 else 2
 codes = onp.synthetic_codes(n, 101, seed=3)

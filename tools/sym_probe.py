@@ -9,11 +9,11 @@ import torch
 import torch.distributed as dist
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-for p in (os.path.join(ROOT, "kernel-methods-for-genomics_b200"), os.path.join(ROOT, "oracle")):
+for p in (os.path.join(ROOT, "kernel-methods-for-genomics_b200"), os.path.join(ROOT, "tools")):
     sys.path.insert(0, p)
 from kmg import device as kd  # noqa: E402
 from kmg import dist as kdist  # noqa: E402
-import oracle_np as onp  # noqa: E402
+import _inputs as onp  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--size", dest="n", type=int, default=100000)
