@@ -189,9 +189,14 @@ constexpr size_t D2H_SLOT_BYTES = 8u << 20;
 struct PinnedRing {
     void* buf[D2H_SLOTS] = {};
     cudaEvent_t ev[D2H_SLOTS] = {};
+    std::future<int> fut[D2H_SLOTS];  // the copy thread that empties each slot
+    int slot = 0;                     // next slot to fill
+    int* h_flags = nullptr;           // mapped pinned ints the device raises (u16 overflow of a block), host view
+    int* d_flags = nullptr;           // ... device view
     bool ready = false;
     std::mutex mu;
 };
+constexpr int D2H_FLAGS = 64;
 PinnedRing g_ring;
 
 int ring_init() {
@@ -200,6 +205,8 @@ int ring_init() {
         KMG_CUDA_CHECK(cudaHostAlloc(&g_ring.buf[i], D2H_SLOT_BYTES, cudaHostAllocDefault));
         KMG_CUDA_CHECK(cudaEventCreateWithFlags(&g_ring.ev[i], cudaEventDisableTiming));
     }
+    KMG_CUDA_CHECK(cudaHostAlloc(reinterpret_cast<void**>(&g_ring.h_flags), D2H_FLAGS * sizeof(int), cudaHostAllocMapped));
+    KMG_CUDA_CHECK(cudaHostGetDevicePointer(reinterpret_cast<void**>(&g_ring.d_flags), g_ring.h_flags, 0));
     g_ring.ready = true;
     return KMG_OK;
 }
@@ -240,7 +247,21 @@ void widen_u16_row(double* __restrict__ dst, const uint16_t* __restrict__ src, i
 // the way into the caller's buffer -- an unnormalised spectrum Gram is integer valued, so shipping the tensor cores'
 // own s32 accumulators halves the PCIe bytes per entry.  dst: host doubles, row stride ldk.
 // src_elem: 8 = doubles, 4 = s32 counts, 2 = u16 counts (both widened exactly).
-int d2h_rows(double* dst, int64_t ldk, const void* src_v, int src_elem, int64_t cols, int64_t rows, cudaStream_t s) {
+// drain = false: returns once every DMA of the block is enqueued on `s` (the source may be overwritten by later work on
+// `s`); the copy threads of the last slots may still be writing `dst` -- call ring_drain() before handing `dst` out.
+int ring_drain_locked() {
+    int err = KMG_OK;
+    for (int i = 0; i < D2H_SLOTS; ++i)
+        if (g_ring.fut[i].valid() && g_ring.fut[i].get() != 0) err = KMG_ERR_CUDA;
+    if (err) kmg_set_error("device-to-host copy failed");
+    return err;
+}
+int ring_drain() {
+    std::lock_guard<std::mutex> lk(g_ring.mu);
+    return ring_drain_locked();
+}
+
+int d2h_rows(double* dst, int64_t ldk, const void* src_v, int src_elem, int64_t cols, int64_t rows, cudaStream_t s, bool drain = true) {
     const bool src_s32 = src_elem != 8;  // "needs widening"
     if (rows <= 0 || cols <= 0) return KMG_OK;
     std::lock_guard<std::mutex> lk(g_ring.mu);
@@ -262,10 +283,10 @@ int d2h_rows(double* dst, int64_t ldk, const void* src_v, int src_elem, int64_t 
         return KMG_OK;
     }
     const int64_t chunk_rows = std::max<int64_t>(1, (int64_t)(D2H_SLOT_BYTES / row_bytes));
-    std::future<int> fut[D2H_SLOTS];
+    std::future<int>* fut = g_ring.fut;
     int err = KMG_OK;
-    int slot = 0;
-    for (int64_t r = 0; r < rows; r += chunk_rows, slot = (slot + 1) % D2H_SLOTS) {
+    for (int64_t r = 0; r < rows; r += chunk_rows, g_ring.slot = (g_ring.slot + 1) % D2H_SLOTS) {
+        const int slot = g_ring.slot;
         const int64_t nr = std::min<int64_t>(chunk_rows, rows - r);
         if (fut[slot].valid() && fut[slot].get() != 0) err = KMG_ERR_CUDA;
         if (err) break;
@@ -292,9 +313,10 @@ int d2h_rows(double* dst, int64_t ldk, const void* src_v, int src_elem, int64_t 
             return 0;
         });
     }
-    for (int i = 0; i < D2H_SLOTS; ++i)
-        if (fut[i].valid() && fut[i].get() != 0) err = KMG_ERR_CUDA;
-    if (err) { kmg_set_error("device-to-host copy failed"); return err; }
+    if (err || drain) {
+        const int e2 = ring_drain_locked();
+        if (err || e2) { kmg_set_error("device-to-host copy failed"); return err ? err : e2; }
+    }
     return KMG_OK;
 }
 
@@ -331,19 +353,40 @@ typedef int (*BlockFn)(void* ctx, int64_t r0, int64_t rows, void* d_out, int64_t
 // If the whole (square, symmetric) matrix fits it is built in one symmetric launch.
 // Second narrowing of a block of s32 counts for the link: if every entry fits 16 bits (checked on the device, exact)
 // the block crosses PCIe as u16 -- 2 bytes per Gram entry instead of 8.  Costs one HBM pass (6 B/entry) and a flag read.
+int narrow_enabled() { return getenv("KMG_D2H_S32") == nullptr; }
+
+// overflow flags: D2H_FLAGS mapped pinned ints shared by all calls of the process; a call owns the slots it acquired
+// (host entry points may run concurrently from several threads: ctypes drops the GIL)
+uint64_t g_flag_busy = 0;
+int flag_acquire() {
+    std::lock_guard<std::mutex> lk(g_ring.mu);
+    if (ring_init() != KMG_OK) return -1;
+    for (int f = 0; f < D2H_FLAGS; ++f)
+        if (!((g_flag_busy >> f) & 1)) { g_flag_busy |= (uint64_t)1 << f; g_ring.h_flags[f] = 0; return f; }
+    return -1;  // none free: the caller ships s32
+}
+void flag_release(int f) {
+    if (f < 0) return;
+    std::lock_guard<std::mutex> lk(g_ring.mu);
+    g_flag_busy &= ~((uint64_t)1 << f);
+}
+
+// enqueue the check-and-pack pass of one block on `s`; flag slot `f` is raised on overflow
+int narrow_launch(const void* d_s32, int64_t count, void* d_u16, int f, cudaStream_t s) {
+    return kmg_ew_narrow_u16(static_cast<const int32_t*>(d_s32), count, static_cast<uint16_t*>(d_u16), g_ring.d_flags + f, s);
+}
+
 int try_narrow(const void* d_s32, int64_t count, DevBuf* narrow, int* elem, cudaStream_t s) {
-    if (getenv("KMG_D2H_S32")) return KMG_OK;
+    if (!narrow_enabled()) return KMG_OK;
     int rc;
-    DevBuf flag;
     if ((rc = narrow->alloc((size_t)count * 2 + 16))) return rc;
-    if ((rc = flag.alloc(sizeof(int)))) return rc;
-    KMG_CUDA_CHECK(cudaMemsetAsync(flag.p, 0, sizeof(int), s));
-    if ((rc = kmg_ew_narrow_u16(static_cast<const int32_t*>(d_s32), count, narrow->as<uint16_t>(), flag.as<int>(), s))) return rc;
-    int h = 0;
-    KMG_CUDA_CHECK(cudaMemcpyAsync(&h, flag.p, sizeof(int), cudaMemcpyDeviceToHost, s));
-    KMG_CUDA_CHECK(cudaStreamSynchronize(s));
-    if (h == 0) *elem = 2;
-    return KMG_OK;
+    const int f = flag_acquire();
+    if (f < 0) return KMG_OK;
+    rc = narrow_launch(d_s32, count, narrow->p, f, s);
+    if (rc == KMG_OK && cudaStreamSynchronize(s) != cudaSuccess) { kmg_set_error("narrow pass failed"); rc = KMG_ERR_CUDA; }
+    if (rc == KMG_OK && g_ring.h_flags[f] == 0) *elem = 2;
+    flag_release(f);
+    return rc;
 }
 
 // out_s32: `fn` writes int32 counts (d2h_rows widens them on the host side of the link).
@@ -356,17 +399,46 @@ int build_to_host(int64_t nr, int64_t nc, bool symmetric, BlockFn fn, void* ctx,
     int64_t br = 0;
     if ((rc = pick_block_rows(nr, nc, &br))) return rc;
     if (br >= nr) {
-        DevBuf out;
+        // The whole block fits.  A large cross-Gram is still built in a few row chunks, all enqueued up front: the host
+        // link (the slow side) starts on chunk 0 while the GPU builds the rest, and the copy threads run across chunk
+        // boundaries (d2h_rows does not drain between chunks).
+        const int nchunks = (!symmetric && nr >= 1024 && (double)nr * (double)nc >= 64e6 && !getenv("KMG_NO_SPLIT")) ? 4 : 1;
+        const int64_t crow = nchunks == 1 ? nr : ((nr + nchunks - 1) / nchunks + 255) / 256 * 256;
+        const bool narrowing = out_s32 && narrow_enabled();
+        DevBuf out, narrow;
         if ((rc = out.alloc((size_t)nr * nc * esz))) return rc;
+        if (narrowing && (rc = narrow.alloc((size_t)nr * nc * 2 + 16))) return rc;
         kmg_trace("build_to_host: output allocated");
-        if ((rc = fn(ctx, 0, nr, out.p, nc, symmetric ? 1 : 0, s0))) return rc;
-        if (getenv("KMG_TRACE")) { cudaStreamSynchronize(s0); kmg_trace("build_to_host: kernel done"); }
-        int elem = out_s32 ? 4 : 8;
-        DevBuf narrow;
-        if (out_s32 && (rc = try_narrow(out.p, nr * nc, &narrow, &elem, s0))) return rc;
-        rc = d2h_rows(K, ldk, elem == 2 ? narrow.p : out.p, elem, nc, nr, s0);
+        cudaEvent_t ev[4] = {};
+        int flag[4] = {-1, -1, -1, -1};
+        int used = 0;
+        for (int64_t r0 = 0; r0 < nr; r0 += crow, ++used) {
+            const int64_t rows = std::min<int64_t>(crow, nr - r0);
+            char* o = static_cast<char*>(out.p) + (size_t)r0 * nc * esz;
+            if ((rc = fn(ctx, r0, rows, o, nc, symmetric ? 1 : 0, s0))) break;
+            if (narrowing && (flag[used] = flag_acquire()) >= 0 &&
+                (rc = narrow_launch(o, rows * nc, static_cast<char*>(narrow.p) + (size_t)r0 * nc * 2, flag[used], s0))) break;
+            if (cudaEventCreateWithFlags(&ev[used], cudaEventDisableTiming) != cudaSuccess || cudaEventRecord(ev[used], s0) != cudaSuccess) {
+                kmg_set_error("build_to_host: event failed"); rc = KMG_ERR_CUDA; ++used; break;
+            }
+        }
+        int c = 0;
+        for (int64_t r0 = 0; rc == KMG_OK && r0 < nr; r0 += crow, ++c) {
+            const int64_t rows = std::min<int64_t>(crow, nr - r0);
+            if (cudaEventSynchronize(ev[c]) != cudaSuccess) { kmg_set_error("build_to_host: kernel failed: %s", cudaGetErrorString(cudaGetLastError())); rc = KMG_ERR_CUDA; break; }
+            if (c == 0) kmg_trace("build_to_host: first chunk done");
+            const int elem = out_s32 ? ((flag[c] >= 0 && g_ring.h_flags[flag[c]] == 0) ? 2 : 4) : 8;
+            const char* src = elem == 2 ? static_cast<char*>(narrow.p) + (size_t)r0 * nc * 2 : static_cast<char*>(out.p) + (size_t)r0 * nc * esz;
+            rc = d2h_rows(K + r0 * ldk, ldk, src, elem, nc, rows, s1, /*drain=*/false);
+        }
+        const int rc2 = ring_drain();
+        if (rc) cudaStreamSynchronize(s0);  // nothing of this call may still run when its buffers and flags are released
+        for (int i = 0; i < 4; ++i) {
+            if (ev[i]) cudaEventDestroy(ev[i]);
+            flag_release(flag[i]);
+        }
         kmg_trace("build_to_host: copied to host");
-        return rc;
+        return rc ? rc : rc2;
     }
     // streamed: two device buffers; the GPU builds block b+1 while block b drains to the host
     DevBuf buf[2];

@@ -218,7 +218,7 @@ __global__ void __launch_bounds__(256) narrow_u16_kernel(const int32_t* __restri
             for (int64_t j = i; j < count; ++j) { bad |= (uint32_t)src[j]; dst[j] = (uint16_t)src[j]; }
         }
     }
-    if (bad >> 16) atomicOr(flag, 1);  // negative values have the top bit set
+    if (bad >> 16) *reinterpret_cast<volatile int*>(flag) = 1;  // negative values have the top bit set; the flag may live in mapped host memory
 }
 
 }  // namespace
