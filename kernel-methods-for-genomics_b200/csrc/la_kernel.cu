@@ -100,51 +100,62 @@ la_kernel(const uint32_t* __restrict__ prow, const uint32_t* __restrict__ pcol, 
     const int steps = L + LP - 1;
     double result = 0.0;
 
+    // Per cell the state is kept as the sums the recursion actually consumes (rows of a lane's strip), plus M and X of
+    // the strip's bottom row for the lane below:
+    //   T = M + X       (Y [i,j] = e^{bd} T[i,j-1] + e^{be} Y[i,j-1])
+    //   S = T + Y       (M [i,j] = e^{b s} (1 + S[i-1,j-1]))
+    //   U = M + X2      (X2[i,j] = U[i-1,j];  Y2[i,j] = U[i,j-1] + Y2[i,j-1];  result = ln(1 + U + Y2))
+    // 10 FP64 operations per cell instead of 12 and five live arrays.  T and U reproduce the written recursion bit for
+    // bit; S associates (M + X) + Y instead of (X + Y) + M (far inside the 1e-12 of the parity tests).  In the max-plus
+    // (Smith-Waterman) variant every one of these regroupings is exact.
     if (!p.smith) {
         // ---------------- affine_align, scaled linear space
-        double M[RPL], X[RPL], Y[RPL], X2[RPL], Y2[RPL];
+        double T[RPL], Y[RPL], U[RPL], Y2[RPL], S[RPL];
 #pragma unroll
-        for (int q = 0; q < RPL; ++q) M[q] = X[q] = Y[q] = X2[q] = Y2[q] = 0.0;
-        double dM = 0.0, dX = 0.0, dY = 0.0;  // row above the strip, previous column
-        int E = 0;                            // stored = true * 2^-E
+        for (int q = 0; q < RPL; ++q) T[q] = Y[q] = U[q] = Y2[q] = S[q] = 0.0;
+        double bM = 0.0, bX = 0.0;  // M, X of the strip's bottom row
+        double dS = 0.0;            // S of the row above the strip, previous column
+        int E = 0;                  // stored = true * 2^-E
         double one_s = 1.0;
         const double ed = p.ed, ee = p.ee;
         int until_check = p.check_every;
 #pragma unroll 1
         for (int t = 0; t < steps; ++t) {
             // bottom row of the lane above, as computed in the previous step (= this lane's column j)
-            double uM = shfl_up_d<LP>(gmask, M[RPL - 1]);
-            double uX = shfl_up_d<LP>(gmask, X[RPL - 1]);
-            double uY = shfl_up_d<LP>(gmask, Y[RPL - 1]);
-            double uX2 = shfl_up_d<LP>(gmask, X2[RPL - 1]);
-            if (gl == 0) uM = uX = uY = uX2 = 0.0;
+            double uM = shfl_up_d<LP>(gmask, bM);
+            double uX = shfl_up_d<LP>(gmask, bX);
+            double uS = shfl_up_d<LP>(gmask, S[RPL - 1]);
+            double uU = shfl_up_d<LP>(gmask, U[RPL - 1]);
+            if (gl == 0) uM = uX = uS = uU = 0.0;
             const int j = t - gl;  // 0-based column
             if (j >= 0 && j < L) {
                 const int yc = ycode_s[group][j];
-                double aM = uM, aX = uX, aX2 = uX2;  // "up"   : (i-1, j)
-                double gM = dM, gX = dX, gY = dY;    // "diag" : (i-1, j-1)
+                double aM = uM, aX = uX, aU = uU;  // "up"   : (i-1, j)
+                double gS = dS;                    // "diag" : (i-1, j-1)
 #pragma unroll
                 for (int q = 0; q < RPL; ++q) {
                     const double a = sub_s[xc[q] | yc];
-                    const double lM = M[q], lX = X[q], lY = Y[q], lX2 = X2[q], lY2 = Y2[q];  // "left": (i, j-1)
-                    const double nM = a * (((one_s + gX) + gY) + gM);
+                    const double lT = T[q], lY = Y[q], lU = U[q], lY2 = Y2[q], lS = S[q];  // "left": (i, j-1)
+                    const double nM = a * (one_s + gS);
                     const double nX = ed * aM + ee * aX;
-                    const double nY = ed * (lM + lX) + ee * lY;
-                    const double nX2 = aM + aX2;
-                    const double nY2 = (lM + lX2) + lY2;
-                    gM = lM; gX = lX; gY = lY;
-                    aM = nM; aX = nX; aX2 = nX2;
-                    M[q] = nM; X[q] = nX; Y[q] = nY; X2[q] = nX2; Y2[q] = nY2;
+                    const double nY = ed * lT + ee * lY;
+                    const double nY2 = lU + lY2;
+                    const double nU = nM + aU;
+                    const double nT = nM + nX;
+                    gS = lS;
+                    aM = nM; aX = nX; aU = nU;
+                    T[q] = nT; Y[q] = nY; U[q] = nU; Y2[q] = nY2; S[q] = nT + nY;
                 }
-                dM = uM; dX = uX; dY = uY;
+                bM = aM; bX = aX;
+                dS = uS;
             }
             if (t == L - 1 + last_lane && gl == last_lane) {
                 // cell (n_x, n_y): this lane's row last_q at column L-1
-                double m = M[0], x2 = X2[0], y2 = Y2[0];
+                double u = U[0], y2 = Y2[0];
 #pragma unroll
                 for (int q = 1; q < RPL; ++q)
-                    if (q == last_q) { m = M[q]; x2 = X2[q]; y2 = Y2[q]; }
-                const double tot = ((one_s + x2) + y2) + m;
+                    if (q == last_q) { u = U[q]; y2 = Y2[q]; }
+                const double tot = (one_s + u) + y2;
                 result = p.inv_beta * (log(tot) + (double)E * 0.6931471805599453094);
             }
             if (--until_check == 0) {
@@ -153,10 +164,8 @@ la_kernel(const uint32_t* __restrict__ prow, const uint32_t* __restrict__ pcol, 
                 int hi = 0;
 #pragma unroll
                 for (int q = 0; q < RPL; ++q) {
-                    hi = max(hi, __double2hiint(M[q]));
-                    hi = max(hi, __double2hiint(X[q]));
-                    hi = max(hi, __double2hiint(Y[q]));
-                    hi = max(hi, __double2hiint(X2[q]));
+                    hi = max(hi, __double2hiint(S[q]));   // S >= T, Y, M, X
+                    hi = max(hi, __double2hiint(U[q]));
                     hi = max(hi, __double2hiint(Y2[q]));
                 }
                 hi = __reduce_max_sync(gmask, hi);
@@ -165,55 +174,57 @@ la_kernel(const uint32_t* __restrict__ prow, const uint32_t* __restrict__ pcol, 
                     const double sc = __hiloint2double((1023 - ex) << 20, 0);  // 2^-ex
 #pragma unroll
                     for (int q = 0; q < RPL; ++q) {
-                        M[q] *= sc; X[q] *= sc; Y[q] *= sc; X2[q] *= sc; Y2[q] *= sc;
+                        T[q] *= sc; Y[q] *= sc; U[q] *= sc; Y2[q] *= sc; S[q] *= sc;
                     }
-                    dM *= sc; dX *= sc; dY *= sc;
+                    bM *= sc; bX *= sc; dS *= sc;
                     E += ex;
                     one_s = (E < 1000) ? __hiloint2double((1023 - E) << 20, 0) : 0.0;  // 2^-E (negligible beyond)
                 }
             }
         }
     } else {
-        // ---------------- Smith_Waterman (max-plus), log space
+        // ---------------- Smith_Waterman (max-plus), log space: T = max(M, X), S = max(T, Y), U = max(M, X2)
         const double NI = -INFINITY;
-        double M[RPL], X[RPL], Y[RPL], X2[RPL], Y2[RPL];
+        double T[RPL], Y[RPL], U[RPL], Y2[RPL], S[RPL];
 #pragma unroll
-        for (int q = 0; q < RPL; ++q) M[q] = X[q] = Y[q] = X2[q] = Y2[q] = NI;
-        double dM = NI, dX = NI, dY = NI;
+        for (int q = 0; q < RPL; ++q) T[q] = Y[q] = U[q] = Y2[q] = S[q] = NI;
+        double bM = NI, bX = NI, dS = NI;
         const double bd = p.bd, be = p.be;
 #pragma unroll 1
         for (int t = 0; t < steps; ++t) {
-            double uM = shfl_up_d<LP>(gmask, M[RPL - 1]);
-            double uX = shfl_up_d<LP>(gmask, X[RPL - 1]);
-            double uY = shfl_up_d<LP>(gmask, Y[RPL - 1]);
-            double uX2 = shfl_up_d<LP>(gmask, X2[RPL - 1]);
-            if (gl == 0) uM = uX = uY = uX2 = NI;
+            double uM = shfl_up_d<LP>(gmask, bM);
+            double uX = shfl_up_d<LP>(gmask, bX);
+            double uS = shfl_up_d<LP>(gmask, S[RPL - 1]);
+            double uU = shfl_up_d<LP>(gmask, U[RPL - 1]);
+            if (gl == 0) uM = uX = uS = uU = NI;
             const int j = t - gl;
             if (j >= 0 && j < L) {
                 const int yc = ycode_s[group][j];
-                double aM = uM, aX = uX, aX2 = uX2;
-                double gM = dM, gX = dX, gY = dY;
+                double aM = uM, aX = uX, aU = uU;
+                double gS = dS;
 #pragma unroll
                 for (int q = 0; q < RPL; ++q) {
                     const double s = sub_s[xc[q] | yc];
-                    const double lM = M[q], lX = X[q], lY = Y[q], lX2 = X2[q], lY2 = Y2[q];
-                    const double nM = s + fmax(fmax(0.0, gX), fmax(gY, gM));
+                    const double lT = T[q], lY = Y[q], lU = U[q], lY2 = Y2[q], lS = S[q];
+                    const double nM = s + fmax(0.0, gS);
                     const double nX = fmax(bd + aM, be + aX);
-                    const double nY = fmax(fmax(bd + lM, bd + lX), be + lY);
-                    const double nX2 = fmax(aM, aX2);
-                    const double nY2 = fmax(fmax(lM, lX2), lY2);
-                    gM = lM; gX = lX; gY = lY;
-                    aM = nM; aX = nX; aX2 = nX2;
-                    M[q] = nM; X[q] = nX; Y[q] = nY; X2[q] = nX2; Y2[q] = nY2;
+                    const double nY = fmax(bd + lT, be + lY);   // bd + max(M, X) == max(bd + M, bd + X): rounding is monotone
+                    const double nY2 = fmax(lU, lY2);
+                    const double nU = fmax(nM, aU);
+                    const double nT = fmax(nM, nX);
+                    gS = lS;
+                    aM = nM; aX = nX; aU = nU;
+                    T[q] = nT; Y[q] = nY; U[q] = nU; Y2[q] = nY2; S[q] = fmax(nT, nY);
                 }
-                dM = uM; dX = uX; dY = uY;
+                bM = aM; bX = aX;
+                dS = uS;
             }
             if (t == L - 1 + last_lane && gl == last_lane) {
-                double m = M[0], x2 = X2[0], y2 = Y2[0];
+                double u = U[0], y2 = Y2[0];
 #pragma unroll
                 for (int q = 1; q < RPL; ++q)
-                    if (q == last_q) { m = M[q]; x2 = X2[q]; y2 = Y2[q]; }
-                result = p.inv_beta * fmax(fmax(0.0, x2), fmax(y2, m));
+                    if (q == last_q) { u = U[q]; y2 = Y2[q]; }
+                result = p.inv_beta * fmax(0.0, fmax(u, y2));
             }
         }
     }
