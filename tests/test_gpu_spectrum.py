@@ -178,6 +178,24 @@ def test_host_link_transports(kh, dna, monkeypatch):
     assert np.array_equal(kh.spectrum_gram(c[:300], ks, cols=c), want[:300])
 
 
+def test_host_chunked_cross_gram(kh, kd):
+    """A cross-Gram of >= 1024 rows and >= 64e6 entries is built in row chunks that drain to the host while the GPU
+    builds the next ones; one chunk holds an entry > 65535 and crosses as s32, the others as u16.  Same bits as the
+    device-resident GEMM."""
+    ks = [1, 2, 3, 4, 5, 6, 7]
+    c = onp.synthetic_codes(60000, 101, seed=11)
+    rows = c[:1100].copy()
+    rows[700] = 0
+    c[5] = 0
+    got = kh.spectrum_gram(rows, ks, cols=c)
+    phi_c = kd.spectrum_phi(kd.pack(c, 0), 101, ks)
+    phi_r = kd.spectrum_phi(kd.pack(rows, 0), 101, ks)
+    want = kd.gram_i8(phi_r, phi_c, out_dtype=1).cpu().numpy()
+    assert got[700, 5] == 67256 and got.shape == (1100, 60000)
+    assert np.array_equal(got, want)
+    assert np.array_equal(got[:16, :64], onp.spectrum_gram(np.concatenate((rows[:16], c[:64])), ks)[:16, 16:])
+
+
 @pytest.mark.parametrize("world", [1, 2, 3, 4, 8])
 def test_sharded_symmetric_gram_single_device(kd, world):
     """kmg_gram_i8_sharded_dev with every part's buffer on this one GPU: each part's launch computes about half of its
