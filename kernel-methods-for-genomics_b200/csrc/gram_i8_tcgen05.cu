@@ -626,10 +626,12 @@ int env_int(const char* name, int dflt) {
 constexpr int COUNTER_SLOTS = 1024;
 uint32_t* g_counters[64] = {};
 unsigned g_counter_next[64] = {};
+std::mutex g_counter_mu;
 int get_counter(cudaStream_t stream, uint32_t** out) {
     int dev = 0;
     KMG_CUDA_CHECK(cudaGetDevice(&dev));
     dev &= 63;
+    std::lock_guard<std::mutex> lk(g_counter_mu);  // host entry points may run from several threads
     if (g_counters[dev] == nullptr) KMG_CUDA_CHECK(cudaMalloc(&g_counters[dev], COUNTER_SLOTS * sizeof(uint32_t)));
     uint32_t* c = g_counters[dev] + (g_counter_next[dev]++ % COUNTER_SLOTS);
     KMG_CUDA_CHECK(cudaMemsetAsync(c, 0, sizeof(uint32_t), stream));

@@ -146,3 +146,27 @@ def test_streamed_block_rows_equal_single_launch():
         subprocess.run([sys.executable, "-c", code, path], check=True, env=env, timeout=600)
         outs.append(np.load(path))
     assert np.array_equal(outs[0], outs[1])
+
+
+def test_concurrent_host_calls_from_threads(kh):
+    """ctypes drops the GIL inside libkmg: host entry points called from several Python threads at once share the
+    pinned ring, the overflow flags, the buffer caches and the wave counters, and must return the sequential results."""
+    import threading
+    ks = list(range(1, 8))
+    data = [onp.synthetic_codes(1500 + 200 * i, 101, seed=40 + i) for i in range(4)]
+    jobs = [lambda d=d: kh.spectrum_gram(d, ks) for d in data[:2]]
+    jobs += [lambda d=data[2]: kh.wd_gram(d[:800], 10), lambda d=data[3]: kh.mismatch_gram(d[:600], 10, 1),
+             lambda d=data[0]: kh.spectrum_gram(d[:1200], ks, cols=onp.synthetic_codes(56000, 101, seed=50))]
+    want = [j() for j in jobs]
+    got = [None] * len(jobs)
+
+    def run(i):
+        got[i] = jobs[i]()
+    for _ in range(2):
+        threads = [threading.Thread(target=run, args=(i,)) for i in range(len(jobs))]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join(timeout=300)
+        for i in range(len(jobs)):
+            assert got[i] is not None and np.array_equal(got[i], want[i]), i
