@@ -139,6 +139,11 @@ int kmg_gram_sharded_stage_bytes(int n_parts, const int64_t* part_row0, int part
 int kmg_gram_i8_sharded_dev(const int8_t* d_phi, int64_t n, int64_t width, int64_t ld_phi, int n_parts, int part,
                             const int64_t* part_row0, void* const* part_out, int64_t ldo, int out_dtype, const double* d_sd,
                             void* d_stage, int64_t* computed_entries, void* stream);
+/* Diagnostic: the int8 tensor-core peak of this GPU as this library can drive it -- iters x 4 back-to-back
+ * tcgen05.mma.cta_group::2.kind::i8 (256 x 256 x 32) per CTA pair, operands resident in shared memory, no loads, no
+ * epilogue.  Enqueues only; the caller times the stream.  *ops = int8 operations issued.  bench.py's roofline
+ * denominator (MEASURED_PEAKS.json has no int8 entry). */
+int kmg_mma_peak_i8_dev(int iters, int64_t* ops, void* stream);
 /* the assignment rule itself (host utility, no GPU): 1 when part a computes tile (I, J) of the global 256-grid whose
  * columns belong to part b; exactly one of a:(I,J) and b:(J,I) is 1 for I != J */
 int kmg_gram_sharded_takes_host(int n_parts, const int64_t* part_row0, int a, int b, int64_t I, int64_t J);

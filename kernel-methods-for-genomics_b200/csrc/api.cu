@@ -1117,6 +1117,13 @@ int kmg_gram_i8_sharded_dev(const int8_t* d_phi, int64_t n, int64_t width, int64
     return KMG_OK;
 }
 
+// Measured int8 tensor-core peak (mma_peak.cu): enqueue `iters` x 4 back-to-back MMAs per CTA pair; the caller times it.
+int kmg_mma_peak_i8_dev(int iters, int64_t* ops, void* stream) {
+    int rc = require_device();
+    if (rc) return rc;
+    return kmg_mma_peak_i8_launch(iters, ops, (cudaStream_t)stream);
+}
+
 int kmg_gram_sharded_takes_host(int n_parts, const int64_t* part_row0, int a, int b, int64_t I, int64_t J) {
     KMG_REQUIRE(n_parts >= 1 && n_parts <= KMG_MAX_PARTS && part_row0 && a >= 0 && a < n_parts && b >= 0 && b < n_parts, KMG_ERR_ARG,
                 "gram_sharded_takes: bad arguments");

@@ -61,6 +61,7 @@ PROTOTYPES = {
     "kmg_gram_i8_dev": (_i32, [_vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _vp, _i64, _i32, _i32, _vp, _vp, _i32, _vp]),
     "kmg_gram_sharded_stage_bytes": (_i32, [_i32, _vp, _i32, _i32, _vp]),
     "kmg_gram_i8_sharded_dev": (_i32, [_vp, _i64, _i64, _i64, _i32, _i32, _vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp]),
+    "kmg_mma_peak_i8_dev": (_i32, [_i32, _vp, _vp]),
     "kmg_gram_sharded_takes_host": (_i32, [_i32, _vp, _i32, _i32, _i64, _i64]),
     "kmg_ipc_export": (_i32, [_vp, _vp]),
     "kmg_ipc_open": (_i32, [_vp, _vp]),

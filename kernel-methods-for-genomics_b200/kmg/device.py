@@ -118,6 +118,21 @@ def gram_i8_sharded(phi, part_row0, part, part_ptrs, ldo, out_dtype=KMG_OUT_F64,
     return computed.value
 
 
+def mma_peak_i8(iters=20000, repeats=3):
+    """Measured int8 tensor-core peak in TOP/s (kmg_mma_peak_i8_dev timed with CUDA events on the current stream)."""
+    _dev()
+    ops = C.c_int64(0)
+    best = 0.0
+    for _ in range(repeats + 1):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        check(_cabi.lib().kmg_mma_peak_i8_dev(int(iters), C.byref(ops), _stream()))
+        e1.record()
+        torch.cuda.synchronize()
+        best = max(best, ops.value / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+    return best
+
+
 def gram_i8_simt(phi_rows, phi_cols):
     rows, W = phi_rows.shape
     cols = phi_cols.shape[0]

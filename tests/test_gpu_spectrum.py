@@ -259,3 +259,20 @@ def test_full_size_properties(kd):
     assert torch.equal(K[rows].to(torch.float64).sum(1), want)
     K1 = kd.gram_i8(phi[:4096], phi, out_dtype=0, m_sub=1)
     assert torch.equal(K1, K[:4096])
+
+
+def test_mma_peak_microbenchmark(kd):
+    """bench.py's roofline denominator: the back-to-back tcgen05.mma.kind::i8 rate must be a plausible B200 figure and
+    at least what the full GEMM (loads + epilogue included) reaches."""
+    import torch
+    peak = kd.mma_peak_i8(iters=50000, repeats=2)
+    assert 3000.0 < peak < 6000.0, peak
+    c = onp.synthetic_codes(8192, 101, seed=3)
+    phi = kd.spectrum_phi(kd.pack(c, 0), 101, list(range(1, 8)))
+    out = torch.empty((8192, 8192), dtype=torch.int32, device="cuda")
+    best = 0.0
+    for _ in range(3):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); kd.gram_i8(phi, phi, out_dtype=0, out=out); e1.record(); torch.cuda.synchronize()
+        best = max(best, 2.0 * 8192 * 8192 * phi.shape[1] / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+    assert best < peak * 1.02, (best, peak)
