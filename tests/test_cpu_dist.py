@@ -124,3 +124,30 @@ def test_symmetric_shard_assignment_covers_every_tile_once():
             assert share.min() > 0.40 and share.max() < 0.62, (n, world, share)
     with pytest.raises(ValueError):
         kdist.sym_bounds(500, 4)
+
+
+def test_sharded_plan_matches_the_assignment_rule():
+    """The staged sharded build launches one GEMM per peer block (api.cu sharded_plan); the staging it asks for
+    (kmg_gram_sharded_stage_bytes, no GPU needed) must hold exactly the entries the assignment rule gives the part in
+    other parts' columns -- the two descriptions of the same partition cannot drift apart."""
+    import ctypes as C
+    from kmg import _cabi
+    from kmg import dist as kdist
+    lib = _cabi.lib()
+    for n, world in ((2048, 2), (3000, 2), (3000, 3), (5000, 4), (9000, 8), (25000, 8), (7000, 5)):
+        bounds = kdist.sym_bounds(n, world)
+        bd = np.ascontiguousarray(bounds, np.int64)
+        tiles = -(-n // 256)
+        owner = [max(p for p in range(world) if bounds[p] <= 256 * t) for t in range(tiles)]
+        width = [min(256, n - 256 * t) for t in range(tiles)]
+        for a in range(world):
+            want = 0
+            for I in range(tiles):
+                if owner[I] != a:
+                    continue
+                for J in range(tiles):
+                    if owner[J] != a and kdist.sym_takes(bounds, a, owner[J], I, J):
+                        want += width[I] * width[J]
+            got = C.c_int64(-1)
+            _cabi.check(lib.kmg_gram_sharded_stage_bytes(world, bd.ctypes.data_as(C.c_void_p), a, 1, C.byref(got)))
+            assert want * 8 <= got.value <= want * 8 + 256 * world, (n, world, a, want * 8, got.value)
