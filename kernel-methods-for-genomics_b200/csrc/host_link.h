@@ -1,0 +1,19 @@
+// host_link.h -- device -> host delivery of Gram blocks (host_link.cu): pinned staging ring with copy / widening threads,
+// narrow integer transports, recycled result blocks, and the block-row driver behind every `*_host` builder.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+// builds rows [r0, r0 + rows) of the Gram into d_out (row stride ldo elements) on stream s
+typedef int (*BlockFn)(void* ctx, int64_t r0, int64_t rows, void* d_out, int64_t ldo, int symmetric, cudaStream_t s);
+
+// Build an nr x nc Gram on the device -- whole, in row chunks, or streamed through two buffers when it does not fit --
+// and deliver it as doubles into K (row stride ldk).  out_s32: `fn` writes int32 counts, which cross the link as u16
+// or s32 and are widened by the copy threads.
+int kmg_hl_build_to_host(int64_t nr, int64_t nc, bool symmetric, BlockFn fn, void* ctx, double* K, int64_t ldk, bool out_s32 = false);
+// widest row (in bytes on the link) the staging ring takes
+size_t kmg_hl_slot_bytes();
+// recycled host blocks behind kmg_host_alloc / kmg_host_free / kmg_release
+int kmg_hl_host_alloc(int64_t bytes, void** ptr);
+int kmg_hl_host_free(void* ptr);
+void kmg_hl_trim_pool();
