@@ -200,7 +200,7 @@ __global__ void __launch_bounds__(256) weighted_dot_partial_kernel(const double*
     if (threadIdx.x == 0) partial[i] = acc * wi;
 }
 
-// s32 counts -> u16 for the host link (api.cu d2h_rows widens them back to double): 8 entries per thread, 16-byte
+// s32 counts -> u16 for the host link (host_link.cu d2h_rows widens them back to double): 8 entries per thread, 16-byte
 // stores.  Any entry outside 0..65535 raises *flag and the caller ships the s32 block instead.
 __global__ void __launch_bounds__(256) narrow_u16_kernel(const int32_t* __restrict__ src, int64_t count, uint16_t* __restrict__ dst,
                                                          int* __restrict__ flag) {
