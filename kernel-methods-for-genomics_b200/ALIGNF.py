@@ -1,16 +1,18 @@
 """
 ALIGNF.py -- drop-in for the reference's ALIGNF.py with the Gram-side algebra on the GPU.
 
-Same class, constructor and method names as the reference (ALIGNF.py:8-113).  What moves to libkmg.so:
-  * sub-block selection K[idx][:, idx] + centring of every kernel (ALIGNF.py:28-29, 36-41),
-  * a_i = <Kc_i, y y'>_F (ALIGNF.py:43-48) and M_ij = <Kc_i, Kc_j>_F (ALIGNF.py:50-58)
-    -- one call, `kmg_alignf_stats_host`, the centred sub-blocks never leave the device,
-  * the final combination sum_i u*_i K_i over the full kernels (ALIGNF.py:91-94), `kmg_combine_host`.
-What stays exactly as in the reference: the p-dimensional (p <= ~10) L-BFGS-B problem v'Mv - 2v'a, v >= 0
-(ALIGNF.py:60-89) -- it is outside the hot path and runs unchanged on our a and M.
+Public surface as in the reference (ALIGNF.py:8-113): class `ALIGNF(X, y, ID, kernels)` with `center`, `get_a`,
+`get_M`, `loss`, `jac`, `callbackF`, `get_v`, `get_K`, attributes `a`, `M`, `u_star`, and `aligned_kernels(methods)`.
 
-The reference's own ALIGNF.py also works unchanged on top of this package's `kernels.center_K`; this module
-additionally keeps p centred n_fit x n_fit matrices and their p^2 pairwise products off the host.
+What runs in libkmg.so:
+  * the sub-block selection K[idx][:, idx] and the centring of every kernel (ALIGNF.py:28-29, 36-41),
+  * a_i = <Kc_i, y y'>_F (ALIGNF.py:43-48) and M_ij = <Kc_i, Kc_j>_F (ALIGNF.py:50-58): one call,
+    `kmg_alignf_stats_host`; the centred sub-blocks and their p^2 pairwise products never leave the device,
+  * the final combination sum_i u*_i K_i over the full kernels (ALIGNF.py:91-94): `kmg_combine_host`.
+What stays on the host: the p-dimensional (p <= ~10) non-negative quadratic programme  min_v v'Mv - 2 v'a, v >= 0
+(ALIGNF.py:60-89) -- solver code, outside the hot path.  It is solved here with the same
+method and settings the reference uses (SciPy's L-BFGS-B from a standard-normal start, pgtol 1e-6, one progress
+line per iteration), written independently.
 """
 import numpy as np
 from scipy.optimize import fmin_l_bfgs_b
@@ -18,40 +20,40 @@ from scipy.optimize import fmin_l_bfgs_b
 from kmg import host as _host
 
 
+def _rows_of(ID, wanted):
+    """Position in `ID` of every Id in `wanted` (ALIGNF.py:27); duplicates in ID resolve as np.where does."""
+    pos = [np.flatnonzero(ID == w) for w in wanted]
+    return np.array(pos).squeeze()
+
+
 class ALIGNF():
-    """
-    Implementation of ALIGNF algorithm.
-    Reference: "Algorithms for Learning Kernels Based on Centered Alignment", Cortes et al. (2009)
-    """
+    """Centred-alignment kernel learning (Cortes, Mohri, Rostamizadeh): weights u* maximising the alignment of
+    sum_i u_i K_i with the label kernel y y', from the statistics a and M of the centred training sub-blocks."""
+
     def __init__(self, X, y, ID, kernels):
-        """
-        :param X: pd.DataFrame, training features
-        :param y: pd.DataFrame, training labels
-        :param ID: np.array, Ids (for ordering)
-        :param kernels: list of kernels
-        """
-        self.X = X
+        """X, y: training features / labels (DataFrames with 'Id', 'Bound'); ID: Ids in kernel order; kernels: list of
+        (n, n) float64 Grams."""
+        self.X, self.ID, self.kernels = X, ID, kernels
         self.y = y.loc[:, 'Bound']
-        self.ID = ID
-        self.kernels = kernels
-        self.Id_X = np.array(X.loc[:, 'Id'])
-        self.idx = np.array([np.where(self.ID == self.Id_X[i])[0] for i in range(len(self.Id_X))]).squeeze()  # ALIGNF.py:27
-        self.p = len(self.kernels)
+        self.Id_X = X.loc[:, 'Id'].to_numpy()
+        self.idx = _rows_of(self.ID, self.Id_X)
+        self.p = len(kernels)
         self.Nfeval = 1
-        print('Centering kernels...')
-        print('Computing vector a...')
-        print('Computing matrix M...')
-        a, M = _host.alignf_stats(self.kernels, np.atleast_1d(self.idx), np.asarray(self.y, dtype=np.float64))
-        self.a = a.T
-        self.M = M
+        for stage in ('Centering kernels...', 'Computing vector a...', 'Computing matrix M...'):
+            print(stage)
+        a, M = _host.alignf_stats(kernels, np.atleast_1d(self.idx), np.asarray(self.y, dtype=np.float64))
+        self.a, self.M = a.T, M
         self.u_star = self.get_v()
 
+    # ---- pieces of the reference's interface that callers may still reach for
     @property
     def Y(self):
-        return np.outer(self.y, self.y)  # ALIGNF.py:23 (only materialised if a caller asks for it)
+        """y y' (ALIGNF.py:23); only materialised on request -- a uses it in fused form on the device."""
+        y = np.asarray(self.y, dtype=np.float64)
+        return y[:, None] * y[None, :]
 
     def center(self, kernels):
-        """ALIGNF.py:36-41 (kept for API compatibility; the constructor uses the fused path)."""
+        """Centred copies of `kernels` (ALIGNF.py:36-41); the constructor itself uses the fused statistics call."""
         print('Centering kernels...')
         return [_host.center(np.ascontiguousarray(K, dtype=np.float64)) for K in kernels]
 
@@ -61,44 +63,43 @@ class ALIGNF():
     def get_M(self):
         return self.M
 
+    # ---- the small QP over the weights
     def loss(self, v):
-        return np.dot(v.T, np.dot(self.M, v)) - 2 * np.dot(v, self.a)  # ALIGNF.py:60-61
+        """v'Mv - 2 v'a (ALIGNF.py:60-61)."""
+        return float(v @ self.M @ v - 2.0 * (v @ self.a))
 
     def jac(self, v):
-        return 2 * np.dot(self.M, v) - 2 * self.a  # ALIGNF.py:63-64
+        """Gradient of `loss` (ALIGNF.py:63-64)."""
+        return 2.0 * (self.M @ v - self.a)
 
     def callbackF(self, Xi, Yi=0):
-        """ALIGNF.py:66-79."""
-        if self.Nfeval == 1:
-            self.L = self.loss(Xi)
-            print('Iteration {0:2.0f} : loss={1:8.4f}'.format(self.Nfeval, self.L))
-        else:
-            l_next = self.loss(Xi)
-            print('Iteration {0:2.0f} : loss={1:8.4f}, tol={2:8.4f}'.format(self.Nfeval, l_next, abs(self.L - l_next)))
-            self.L = l_next
+        """One progress line per L-BFGS-B iteration: the loss and, from the second one on, its change."""
+        now = self.loss(Xi)
+        line = 'Iteration {0:2.0f} : loss={1:8.4f}'.format(self.Nfeval, now)
+        if self.Nfeval > 1:
+            line += ', tol={0:8.4f}'.format(abs(self.L - now))
+        print(line)
+        self.L = now
         self.Nfeval += 1
 
     def get_v(self):
-        """ALIGNF.py:81-89 -- unchanged (random init, bounds v >= 0, pgtol 1e-6)."""
+        """argmin of `loss` over v >= 0, scaled to unit Euclidean norm (ALIGNF.py:81-89)."""
         print('Gradient descent...')
-        v0 = np.random.randn(self.p)
-        bounds = [[0, float(np.inf)]] * self.p
-        res = fmin_l_bfgs_b(self.loss, v0, fprime=self.jac, bounds=bounds, pgtol=1e-6, callback=self.callbackF)
-        v_star = res[0]
-        return v_star / np.linalg.norm(v_star)
+        start = np.random.randn(self.p)
+        v, _, _ = fmin_l_bfgs_b(self.loss, start, fprime=self.jac, bounds=[(0.0, None)] * self.p, pgtol=1e-6,
+                                callback=self.callbackF)
+        return v / np.sqrt(v @ v)
 
     def get_K(self):
-        """ALIGNF.py:91-94 -- Km = sum_i u*_i K_i over the full, uncentred kernels."""
-        print('Alignment vector : ', self.u_star, '\n-------------------------------------------------------------')
+        """Km = sum_i u*_i K_i over the full, uncentred kernels (ALIGNF.py:91-94)."""
+        print('Alignment vector : ', self.u_star, '\n' + '-' * 61)
         return _host.combine(self.kernels, self.u_star, degree=1)
 
 
 def aligned_kernels(methods):
-    """ALIGNF.py:97-113 -- needs the reference's `utils` module on sys.path (data loading is out of scope)."""
+    """One ALIGNF combination per data set (ALIGNF.py:97-113).  Loading the data is the reference's `utils` module's
+    business (out of scope here): it has to be importable."""
     import utils
     data, data1, data2, data3, kernels, ID = utils.get_all_data(methods)
-    aligned_k = []
-    for d in [data1, data2, data3]:
-        X, y, _, _, _ = d
-        aligned_k.append(ALIGNF(X, y, ID, kernels).get_K())
-    return data, data1, data2, data3, aligned_k, ID
+    combined = [ALIGNF(d[0], d[1], ID, kernels).get_K() for d in (data1, data2, data3)]
+    return data, data1, data2, data3, combined, ID

@@ -1,15 +1,19 @@
 """
 NLCKernels.py -- drop-in for the reference's NLCKernels.py with the Gram-side algebra on the GPU.
 
-Same class, constructor and method names as the reference (NLCKernels.py:12-100).  What moves to libkmg.so:
+Public surface as in the reference (NLCKernels.py:12-100): class `NLCK(X, y, ID, kernels, C, eps, degree)` with
+`normalize_kernels`, `svm_step`, `grad`, `normalize`, `fit`, `get_K`.
+
+What runs in libkmg.so:
   * normalize_kernels: normalize_K of every kernel, in place (NLCKernels.py:43-48),
   * the K-line of svm_step, (sum_m u_m K_m) ** degree on the fit sub-blocks (NLCKernels.py:52),
   * grad: -degree * alpha' ((sum u K)^(degree-1) o K_m) alpha for every m (NLCKernels.py:61-66),
     -- both on fit sub-blocks uploaded once and kept resident in HBM (kmg/resident.py) for all iterations,
   * get_K: (sum_m u*_m K_m) ** degree followed by normalize_K over the full kernels (NLCKernels.py:97-99).
-What stays as in the reference: the cvxopt QP of svm_step (NLCKernels.py:53-59) and the projected-gradient loop
-(NLCKernels.py:68-92) -- solver code, outside the hot path.  cvxopt is imported lazily, so
-everything except svm_step/fit works without it.
+What stays on the host: the C-SVM dual of svm_step (a cvxopt QP, NLCKernels.py:53-59) and the projected-gradient loop
+over the p weights (NLCKernels.py:68-92) -- solver code, outside the hot path, written here
+independently with the reference's update rule and settings.  cvxopt is imported lazily, so everything except
+svm_step / fit works without it.
 """
 import numpy as np
 
@@ -19,24 +23,23 @@ from kmg import resident as _res
 
 
 class NLCK():
-    """
-    Implementation of NLCK algorithm.
-    Reference : "Learning Non-Linear Combinations of Kernels", Cortes et al. (2009)
-    """
+    """Non-linear (polynomial) combination of kernels (Cortes, Mohri, Rostamizadeh): projected gradient on the weights
+    u of K_u = (sum_m u_m K_m)^degree, every step solving the C-SVM dual for the current K_u."""
+
     def __init__(self, X, y, ID, kernels, C=1e-5, eps=1e-8, degree=2):
-        self.X = X
+        """X, y: training features / labels (DataFrames with 'Id', 'Bound'); ID: Ids in kernel order; kernels: list of
+        (n, n) float64 Grams (normalised in place); C: SVM box constant; eps: stopping threshold on the weight update;
+        degree: order of the polynomial combination."""
+        self.X, self.ID = X, ID
         self.y = y.loc[:, 'Bound']
         self.n = y.shape[0]
-        self.ID = ID
         self.kernels = self.normalize_kernels(kernels)
-        self.Id_X = np.array(X.loc[:, 'Id'])
-        self.idx = np.array([np.where(self.ID == self.Id_X[i])[0] for i in range(len(self.Id_X))]).squeeze()
+        self.Id_X = X.loc[:, 'Id'].to_numpy()
+        self.idx = np.array([np.flatnonzero(self.ID == w) for w in self.Id_X]).squeeze()  # NLCKernels.py:35
         self.kernels_fit = [np.ascontiguousarray(K[self.idx][:, self.idx]) for K in self.kernels]  # NLCKernels.py:36
         self.p = len(self.kernels_fit)
-        self.C = C
+        self.C, self.eps, self.degree = C, eps, degree
         self.lbda = 1 / (2 * self.C * self.n)
-        self.eps = eps
-        self.degree = degree
         self._fit_dev = None  # fit sub-blocks resident in HBM for the whole projected-gradient loop
 
     def _resident(self):
@@ -47,61 +50,59 @@ class NLCK():
         return self._fit_dev
 
     def normalize_kernels(self, kernels):
-        """NLCKernels.py:43-48 (normalize_K mutates its argument and returns it)."""
-        new_kernels = []
-        for k, K in enumerate(kernels):
-            print('Normalizing kernel {}...'.format(k + 1))
-            new_kernels.append(normalize_K(K))
-        return new_kernels
+        """normalize_K of every kernel (it mutates its argument and returns it, NLCKernels.py:43-48)."""
+        out = []
+        for number, K in enumerate(kernels, start=1):
+            print('Normalizing kernel {}...'.format(number))
+            out.append(normalize_K(K))
+        return out
 
     def svm_step(self, u):
-        """NLCKernels.py:50-59 -- the Gram line on the GPU, the QP in cvxopt as in the reference."""
-        from cvxopt import matrix, spmatrix, solvers
+        """Dual variables of the C-SVM on K_u (NLCKernels.py:50-59): min 1/2 a'K_u a - y'a  s.t. 0 <= y_i a_i <= C.
+        K_u comes from the device; the QP is cvxopt's, as in the reference."""
+        from cvxopt import matrix, solvers, spmatrix
         solvers.options['show_progress'] = False
-        r, o, z = np.arange(self.n), np.ones(self.n), np.zeros(self.n)
         grams, _, out = self._resident()
-        K = _res.combine(grams, u, degree=self.degree, out=out).to_host()
-        P = matrix(K.astype(float), tc='d')
-        q = matrix(-self.y, tc='d')
-        G = spmatrix(np.r_[self.y, -self.y], np.r_[r, r + self.n], np.r_[r, r], tc='d')
-        h = matrix(np.r_[o * self.C, z], tc='d')
-        sol = solvers.qp(P, q, G, h)
-        return np.ravel(sol['x'])
+        K_u = _res.combine(grams, u, degree=self.degree, out=out).to_host()
+        y = np.asarray(self.y, dtype=float)
+        n, pos = self.n, np.arange(self.n)
+        # the 2n box rows  y_i a_i <= C  and  -y_i a_i <= 0  as one sparse matrix
+        box = spmatrix(np.concatenate((y, -y)), np.concatenate((pos, pos + n)), np.concatenate((pos, pos)), tc='d')
+        rhs = matrix(np.concatenate((np.full(n, float(self.C)), np.zeros(n))), tc='d')
+        sol = solvers.qp(matrix(K_u, tc='d'), matrix(-y, tc='d'), box, rhs)
+        return np.asarray(sol['x']).ravel()
 
     def grad(self, u, alpha):
-        """NLCKernels.py:61-66."""
+        """d/du_m of the dual objective: -degree * alpha' (K_t o K_m) alpha, K_t = (sum u K)^(degree-1) (NLCKernels.py:61-66)."""
         return self._resident()[1].grad(u, alpha, self.degree)
 
     def normalize(self, u, u0, fnorm):
-        """NLCKernels.py:68-72."""
-        u_s = (u - u0)
-        u_s_norm = u_s / np.sqrt(np.sum(u_s**2))
-        u_s = u_s_norm * fnorm
-        return u_s + u0
+        """Put u on the sphere of radius fnorm around u0 (NLCKernels.py:68-72)."""
+        d = u - u0
+        return u0 + d * (fnorm / np.sqrt((d * d).sum()))
 
     def fit(self, u0=0, fnorm=10, n_iter=20, eta=1):
-        """NLCKernels.py:74-92 -- unchanged."""
-        u = np.ones(self.p)
-        u = self.normalize(u, u0, fnorm)
-        u = np.array([0 if u[i] < 0 else u[i] for i in range(self.p)])
-        score_prev = np.inf
-        for k in range(n_iter):
-            print('Iteration {}, u={}, score={:0.5f}'.format(k, u, score_prev))
+        """Projected gradient (NLCKernels.py:74-92): step along -grad, back onto the sphere, clip at zero; the step
+        shrinks by 0.8 whenever the update grows; stop once the update is below eps."""
+        def project(w):
+            return np.maximum(self.normalize(w, u0, fnorm), 0.0)
+
+        u = project(np.ones(self.p))
+        last_move = np.inf
+        for it in range(n_iter):
+            print('Iteration {}, u={}, score={:0.5f}'.format(it, u, last_move))
             alpha = self.svm_step(u)
-            g = self.grad(u, alpha)
-            u_next = self.normalize(u - eta * g, u0, fnorm)
-            u_next = np.array([0 if u_next[i] < 0 else u_next[i] for i in range(self.p)])
-            score = np.linalg.norm(u_next - u, np.inf)
-            if score > score_prev:
+            nxt = project(u - eta * self.grad(u, alpha))
+            move = np.abs(nxt - u).max()
+            if move > last_move:
                 eta *= 0.8
-            if score < self.eps:
-                return u_next
-            u = u_next
-            score_prev = score.copy()
-        return u_next
+            u, last_move = nxt, move
+            if move < self.eps:
+                break
+        return u
 
     def get_K(self, u0=0, fnorm=1, n_iter=50, eta=1):
-        """NLCKernels.py:94-100."""
+        """(sum_m u*_m K_m) ** degree over the full kernels, normalised (NLCKernels.py:94-100)."""
         u_star = self.fit(u0, fnorm, n_iter, eta)
         print('Alignment vector : ', u_star)
         print('Normalizing final kernel...')
