@@ -39,7 +39,7 @@ int upload_planes(const uint8_t* seqs, int64_t n, int L, int fmt, DevBuf* planes
     if ((rc = raw.alloc((size_t)n * L))) return rc;
     if ((rc = err.alloc(sizeof(int)))) return rc;
     KMG_CUDA_CHECK(cudaMemsetAsync(err.p, 0, sizeof(int), s));
-    KMG_CUDA_CHECK(cudaMemcpyAsync(raw.p, seqs, (size_t)n * L, cudaMemcpyHostToDevice, s));
+    if ((rc = kmg_hl_h2d(raw.p, seqs, (size_t)n * L, s))) return rc;
     if ((rc = kmg_pack_launch(raw.as<uint8_t>(), fmt == KMG_SEQ_ASCII, n, L, planes->as<uint32_t>(), err.as<int>(), s))) return rc;
     int herr = 0;
     KMG_CUDA_CHECK(cudaMemcpyAsync(&herr, err.p, sizeof(int), cudaMemcpyDeviceToHost, s));

@@ -11,6 +11,8 @@ typedef int (*BlockFn)(void* ctx, int64_t r0, int64_t rows, void* d_out, int64_t
 // and deliver it as doubles into K (row stride ldk).  out_s32: `fn` writes int32 counts, which cross the link as u16
 // or s32 and are widened by the copy threads.
 int kmg_hl_build_to_host(int64_t nr, int64_t nc, bool symmetric, BlockFn fn, void* ctx, double* K, int64_t ldk, bool out_s32 = false);
+// pageable host -> device through the pinned slots with parallel copy threads; complete on return
+int kmg_hl_h2d(void* d_dst, const void* h_src, size_t bytes, cudaStream_t s);
 // widest row (in bytes on the link) the staging ring takes
 size_t kmg_hl_slot_bytes();
 // recycled host blocks behind kmg_host_alloc / kmg_host_free / kmg_release
