@@ -394,7 +394,7 @@ def main():
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel, from the ncu --set full
 # capture summarised in profiles/r1_gemm_ncu_full_summary.txt (106.30 GB read + 39.99 GB written; the algorithmic
 # minimum is 40 GB written + 4.4 GB of Phi read once -- the reads are the B panels re-streamed once per 8-row-tile band)
-TRAFFIC_BYTES_PER_LAUNCH = 146_281_768_000
+TRAFFIC_BYTES_PER_LAUNCH = 146_276_310_000
 
 
 def extras(kd, torch, codes, planes, phi, peaks):
