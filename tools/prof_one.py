@@ -1,6 +1,6 @@
 """prof_one.py -- run one kernel configuration a few times (target for ncu)."""
 import argparse, os, sys
-import numpy as np, torch
+import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in (os.path.join(ROOT, "kernel-methods-for-genomics_b200"), os.path.join(ROOT, "tools")):
     sys.path.insert(0, p)

@@ -1,6 +1,6 @@
 """small_probe.py -- latency of the reference-sized calls (BASELINE configs[0]: n = 3000, k = 6) through the host API."""
 import os, sys, time
-import numpy as np
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "kernel-methods-for-genomics_b200")); sys.path.insert(0, os.path.join(ROOT, "tools"))
 from kmg import host as kh

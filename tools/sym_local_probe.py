@@ -1,7 +1,7 @@
 """sym_local_probe.py -- the sharded symmetric GEMM with every part's buffer on ONE GPU (no NVLink): isolates the cost of
 the tile assignment / mirror stores from the cost of storing into peer memory."""
 import os, sys
-import numpy as np, torch
+import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in (os.path.join(ROOT, "kernel-methods-for-genomics_b200"), os.path.join(ROOT, "tools")):
     sys.path.insert(0, p)
