@@ -2,7 +2,8 @@
 host.py -- numpy-level wrappers over the `*_host` entry points of libkmg.so.
 
 Everything here is marshalling: sequences become one contiguous (n, L) byte buffer, Gram matrices
-are caller-owned C-contiguous float64 arrays, and every call ends in the C-ABI (include/kmg.h).
+are C-contiguous float64 arrays handed to the C-ABI (include/kmg.h) to be filled -- large ones over the library's
+recycled host blocks (`_result`), so that repeated builds write into memory that is already mapped.
 No arithmetic on Gram entries happens in Python.
 """
 import ctypes as C
