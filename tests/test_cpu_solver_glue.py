@@ -82,3 +82,41 @@ def test_nlck_projected_gradient_loop(capsys, u0, fnorm, eps):
     u = rng.standard_normal(p)
     assert np.allclose(obj.normalize(u, u0, fnorm), (u - u0) / np.sqrt(np.sum((u - u0) ** 2)) * fnorm + u0, rtol=1e-14, atol=1e-14)
     assert "Iteration 0, u=" in capsys.readouterr().out
+
+
+def test_nlck_svm_step_builds_the_reference_qp(monkeypatch):
+    """svm_step hands cvxopt the same QP as NLCKernels.py:50-59 (P = K_u, q = -y, G = [diag(y); -diag(y)], h = [C 1; 0]).
+    cvxopt is not installed here: a stand-in module records what it is given."""
+    import sys
+    import types
+    import NLCKernels as N
+    seen = {}
+    fake = types.ModuleType("cvxopt")
+    fake.matrix = lambda a, tc='d': np.array(a, dtype=float)
+
+    def spmatrix(vals, rows, cols, tc='d'):
+        rows, cols = np.asarray(rows), np.asarray(cols)
+        dense = np.zeros((rows.max() + 1, cols.max() + 1))
+        dense[rows, cols] = np.asarray(vals, dtype=float)
+        return dense
+    fake.spmatrix = spmatrix
+    fake.solvers = types.SimpleNamespace(options={}, qp=lambda P, q, G, h: seen.update(P=P, q=q, G=G, h=h) or {'x': np.arange(len(q), dtype=float)[:, None]})
+    monkeypatch.setitem(sys.modules, "cvxopt", fake)
+    rng = np.random.default_rng(9)
+    n, p, degree, C = 7, 3, 3, 0.25
+    Ks = [_spd(rng, n) for _ in range(p)]
+    y = np.where(rng.random(n) < 0.5, -1.0, 1.0)
+    u = rng.random(p)
+    import pandas as pd
+    obj = object.__new__(N.NLCK)
+    obj.n, obj.C, obj.degree, obj.y = n, C, degree, pd.Series(y)
+    obj._resident = lambda: (Ks, None, None)
+    monkeypatch.setattr(N._res, "combine", lambda grams, w, degree, out=None: types.SimpleNamespace(
+        to_host=lambda: sum(wi * k for wi, k in zip(w, grams)) ** degree))
+    alpha = obj.svm_step(u)
+    r, o, z = np.arange(n), np.ones(n), np.zeros(n)
+    G = np.zeros((2 * n, n))
+    G[np.r_[r, r + n], np.r_[r, r]] = np.r_[y, -y]
+    assert np.array_equal(seen["P"], np.sum(np.array(Ks) * u[:, None, None], axis=0) ** degree)
+    assert np.array_equal(seen["q"], -y) and np.array_equal(seen["G"], G) and np.array_equal(seen["h"], np.r_[o * C, z])
+    assert fake.solvers.options == {'show_progress': False} and np.array_equal(alpha, np.arange(n, dtype=float))
