@@ -92,14 +92,17 @@ def get_WD_K(X, d):
 # ------------------------------------------------------------------------------------------------
 # Mismatch kernel (kernels.py:161-217)
 # ------------------------------------------------------------------------------------------------
+_DIGITS = str.maketrans('ACGT', '1234')
+
+
 def letter_to_num(x):
-    """kernels.py:178-184."""
-    return x.replace('A', '1').replace('C', '2').replace('G', '3').replace('T', '4')
+    """'ACGT' -> '1234', every other character left as it is (kernels.py:178-184)."""
+    return x.translate(_DIGITS)
 
 
 def format(x):
-    """kernels.py:187-193."""
-    return np.array(list(letter_to_num(x))).astype(int)
+    """Sequence -> int array over 1..4; a non-ACGT character fails in int(), as in the reference (kernels.py:187-193)."""
+    return np.array([int(c) for c in letter_to_num(x)], dtype=int)
 
 
 def get_phi_km(x, k, m, betas):
@@ -187,33 +190,30 @@ def get_gappy_K(X, k, g):
     raise NotImplementedError("GP (gappy) kernel is outside the hot path (SURVEY.md section 2)")
 
 
+# method prefix -> (builder, how to read the '_'-separated fields: (field number, characters to drop, type)).
+# 'WDS' is listed before 'WD' because the latter is a prefix of the former.
+def _dsl():
+    one_int = ((1, 1, int),)
+    two_ints = ((1, 1, int), (2, 1, int))
+    return (
+        ('WDS', get_WDShifts_K, two_ints),
+        ('SP', get_spectrum_K, one_int),
+        ('WD', get_WD_K, one_int),
+        ('MM', get_mismatch_K, two_ints),
+        ('LA', get_LA_K, ((1, 1, float), (2, 1, float), (3, 1, float), (4, len('smith'), int), (5, len('eig'), int))),
+        ('SS', get_string_K, ((1, 1, float), (2, 1, int))),
+        ('GP', get_gappy_K, two_ints),
+    )
+
+
 def select_method(X, method):
-    """kernels.py:461-505 -- same mini-DSL: SP_k{x}, WD_d{x}, MM_k{x}_m{y}, LA_e{x}_d{y}_b{z}_smith{X}_eig{Y},
-    WDS_d{x}_s{y}, SS_l{x}_k{y}, GP_k{x}_g{y}; the first character of every '_' field is stripped."""
-    m = method.split('_')
-    if method[:2] == 'SP':
-        k = int(m[1][1:])
-        K = get_spectrum_K(X, k)
-    elif method[:2] == 'WD' and method[2] != 'S':
-        print(m)
-        d = int(m[1][1:])
-        K = get_WD_K(X, d)
-    elif method[:2] == 'MM':
-        k, m = int(m[1][1:]), int(m[2][1:])
-        K = get_mismatch_K(X, k, m)
-    elif method[:2] == 'LA':
-        e, d, beta = [float(m[i][1:]) for i in range(1, 4)]
-        smith, eig = int(m[4][5:]), int(m[5][3:])
-        K = get_LA_K(X, e, d, beta, smith, eig)
-    elif method[:3] == 'WDS':
-        d, S = int(m[1][1:]), int(m[2][1:])
-        K = get_WDShifts_K(X, d, S)
-    elif method[:2] == 'SS':
-        lbda, k = float(m[1][1:]), int(m[2][1:])
-        K = get_string_K(X, lbda, k)
-    elif method[:2] == 'GP':
-        k, g = int(m[1][1:]), int(m[2][1:])
-        K = get_gappy_K(X, k, g)
-    else:
-        raise NotImplementedError('Method not implemented. Please refer to the documentation for choosing among available methods')
-    return K
+    """The reference's method mini-language (kernels.py:461-505): SP_k{x}, WD_d{x}, WDS_d{x}_s{y}, MM_k{x}_m{y},
+    LA_e{x}_d{y}_b{z}_smith{X}_eig{Y}, SS_l{x}_k{y}, GP_k{x}_g{y}.  Every field carries a one-letter tag (or the words
+    'smith' / 'eig') in front of its value; the tag is dropped, not checked, exactly as the reference does."""
+    fields = method.split('_')
+    for prefix, build, spec in _dsl():
+        if method.startswith(prefix):
+            if prefix == 'WD':
+                print(fields)  # the reference echoes the split method string for this kernel (kernels.py:487)
+            return build(X, *[kind(fields[pos][drop:]) for pos, drop, kind in spec])
+    raise NotImplementedError('Method not implemented. Please refer to the documentation for choosing among available methods')

@@ -110,3 +110,24 @@ def test_result_blocks_are_recycled():
     del b, c
     gc.collect()
     assert _cabi.lib().kmg_release() == 0
+
+
+def test_select_method_parses_the_reference_dsl(monkeypatch, capsys):
+    """kernels.select_method (kernels.py:461-505): every method string of the reference's mini-language reaches the
+    right builder with the right arguments (builders stubbed: no GPU)."""
+    import kernels as km
+    calls = []
+    for name in ("get_spectrum_K", "get_WD_K", "get_mismatch_K", "get_LA_K", "get_WDShifts_K", "get_string_K", "get_gappy_K"):
+        monkeypatch.setattr(km, name, (lambda n: (lambda X, *a: calls.append((n, a)) or n))(name))
+    for method in ("SP_k6", "WD_d10", "WDS_d3_s2", "MM_k10_m1", "LA_e11_d1_b0.5_smith0_eig1", "LA_e11_d1_b0.5_smith1_eig0",
+                   "SS_l0.5_k3", "GP_k5_g1"):
+        km.select_method("X", method)
+    assert calls == [("get_spectrum_K", (6,)), ("get_WD_K", (10,)), ("get_WDShifts_K", (3, 2)), ("get_mismatch_K", (10, 1)),
+                     ("get_LA_K", (11.0, 1.0, 0.5, 0, 1)), ("get_LA_K", (11.0, 1.0, 0.5, 1, 0)), ("get_string_K", (0.5, 3)),
+                     ("get_gappy_K", (5, 1))]
+    assert capsys.readouterr().out == "['WD', 'd10']\n"      # the reference echoes the split string for WD only
+    with pytest.raises(NotImplementedError):
+        km.select_method("X", "XX_k1")
+    assert km.letter_to_num("ACGTN") == "1234N" and km.format("GATTACA").tolist() == [3, 1, 4, 4, 1, 2, 1]
+    with pytest.raises(ValueError):
+        km.format("ACGN")
