@@ -7,17 +7,23 @@ uniform-random 101-bp sequences (PCG64 seed 3), Gram block-rows sharded over the
 (320 GB) does not fit one GPU, so the unit of work is ONE BLOCK-ROW of 25 000 x 200 000 entries per GPU
 (weak scaling: at --gpus 8 the ranks together build the complete 200k x 200k Gram; at --gpus N < 8 they
 build its first N block-rows).  Every rank holds all packed sequences (6.4 MB) and builds its own int8
-feature matrix Phi (4.4 GB) locally: no collective on the data path.
+feature matrix Phi (4.4 GB) locally.
 
-A "step" = spectrum_phi (packed sequences -> Phi, all 200k rows) + the tcgen05 int8 Gram GEMM of the
+The job at every N is the SAME computation: rows [0, N*R) of the Gram.  Its leading N*R x N*R square is symmetric,
+so -- like the reference, which computes the upper triangle and mirrors it (kernels.py:41-45) -- it is built from its
+upper triangle: at N = 1 one symmetric launch with in-place mirror stores, at N > 1 the ranks share the square
+(kmg/dist.py SymmetricShards: each computes about half of its part and delivers the transposed blocks to their
+owners over NVLink); the columns [N*R, n) are a plain cross-Gram launch.
+
+A "step" = spectrum_phi (packed sequences -> Phi, all 200k rows) + the tcgen05 int8 Gram GEMM launches of the
 rank's block-row with the fp64 epilogue, inputs (packed sequences) resident in HBM.  Phi (4.4 GB) and the
 40 GB output are far larger than the 126 MB L2, so no L2 flush is needed between iterations.
 
   python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's CUDA path
   python bench.py --impl reference ...                          # the CPU restatement on the host cores
 
-One JSON line on stdout (rank 0).  Extra keys beyond the contract: "roofline", "cpu_baseline", "kernels"
-(device-resident numbers for the other BASELINE configs at N=1), "clocks".
+One JSON line on stdout (rank 0).  Extra keys beyond the contract: "roofline", "cpu_baseline", "parity", "kernels"
+(device-resident numbers for the other BASELINE configs, every N), "exchange", "clocks".
 """
 import argparse
 import json
@@ -42,6 +48,24 @@ D_ALG = sum(4 ** k for k in KS)  # 21 844 algorithmic feature width (padding to 
 SEED = 3
 NOMINAL_INT8_TOPS = 4500.0
 NOMINAL_HBM_GBS = 7700.0
+
+# Warp-level instructions per Gram entry on the pipe that bounds each pairwise kernel, from the ncu captures summarised in
+# profiles/r2_pipe_instructions.txt (smsp__inst_executed_pipe_*.sum / entries of the launch; uniform-random 101-bp
+# sequences, the code is straight-line per pair so the count does not depend on the block shape).  Thread-level
+# instructions = 32 x these / 32 entries per warp-row... see extras(): achieved = entries/s x INST_PER_ENTRY.
+PIPE_INST = {
+    # kernel: (pipe, thread-level instructions per computed Gram entry, microbenchmark kind that measures the pipe)
+    "mismatch_k10_m1": ("alu", None, "lop3"),
+    "wd_d10": ("alu", None, "lop3"),
+    "la_affine": ("fp64", 10 * 10201.0, "dfma"),  # 10 FP64 instructions per DP cell by construction (csrc/la_kernel.cu)
+}
+try:
+    with open(os.path.join(ROOT, "profiles", "r2_pipe_instructions.json")) as _f:
+        for _k, _v in json.load(_f).items():
+            if _k in PIPE_INST and _v.get("inst_per_entry"):
+                PIPE_INST[_k] = (PIPE_INST[_k][0], float(_v["inst_per_entry"]), PIPE_INST[_k][2])
+except (OSError, ValueError):
+    pass
 
 
 def synthetic_codes(n, seed):
@@ -158,13 +182,22 @@ def reference_arm(args, rank):
     print(json.dumps(line), flush=True)
 
 
-def workload_config(n_gpus, exchange="n/a (1 GPU)", exchange_checked=None):
+def workload_config(n_gpus):
+    """Identical for both arms at a given N: nothing run-dependent goes in here (the exchange report is a separate key)."""
     return {"workload": "BASELINE configs[2]: sum of spectrum kernels k=1..7, n=200000 synthetic 101-bp sequences (PCG64 seed 3), "
                         "one 25000 x 200000 fp64 Gram block-row per GPU",
             "n": N_SEQ, "rows_per_gpu": ROWS_PER_GPU, "block_rows_built": n_gpus, "L": L, "ks": KS, "feature_width": D_ALG,
-            "output": "fp64 (exact integers)", "sharding": f"block-row x{n_gpus} (boundaries on multiples of 256 rows when N > 1), no collective on the data path",
-            "exchange": exchange, "exchange_checked": exchange_checked,
+            "output": "fp64 (exact integers)",
+            "sharding": f"block-row x{n_gpus}; the leading {n_gpus * ROWS_PER_GPU}^2 square is built from its upper triangle and mirrored "
+                        "(kernels.py:41-45), the remaining columns are a plain cross-Gram",
             "l2": "inputs (Phi 4.4 GB) and output (40 GB) exceed the 126 MB L2; no flush needed"}
+
+
+def sym_issued_entries(R):
+    """Entries a symmetric launch over an R x R square issues to the tensor cores: the 256 x 256 tiles that touch col >= row."""
+    t = -(-R // 256)
+    w = [min(256, R - 256 * i) for i in range(t)]
+    return float(sum(w[i] * w[j] for i in range(t) for j in range(i, t)))
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -176,9 +209,11 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-extras", action="store_true", help="skip the per-kernel numbers for the other BASELINE configs")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-e2e", action="store_true", help="(debug) skip the end-to-end leg")
     ap.add_argument("--n", type=int, default=N_SEQ, help="(debug) number of sequences")
     ap.add_argument("--rows", type=int, default=ROWS_PER_GPU, help="(debug) rows per GPU")
-    ap.add_argument("--no-sym", action="store_true", help="N > 1: plain block-rows, no symmetric sharing between the GPUs")
+    ap.add_argument("--no-sym", action="store_true", help="plain block-rows: no symmetric sharing of the leading square")
+    ap.add_argument("--exchange", default=None, help="N > 1: staged | direct | single (default: kmg/dist.py's, KMG_SYM_EXCHANGE)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -203,59 +238,74 @@ def main():
     from kmg._cabi import lib
     lib()
 
+    def allmax(x):
+        t = torch.tensor([float(x)], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def allmin_int(x):
+        t = torch.tensor([int(x)], dtype=torch.int32, device="cuda")
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return int(t.item())
+
     n, R = args.n, args.rows
     peaks = load_peaks()
     codes = synthetic_codes(n, SEED)
     planes = kd.pack(codes, 0)  # every rank holds all packed sequences
     W = kd.phi_width(KS)
     phi = torch.empty((n, W), dtype=torch.int8, device="cuda")
-    # N > 1: the job is rows [0, N*R) of the Gram.  Its leading N*R x N*R square is symmetric, so the ranks share it: each
-    # computes about half of its part of the square and ships the transposed blocks to their owners over NVLink
-    # (kmg/dist.py SymmetricShards: CUDA IPC buffers, one pitched peer copy per block on the copy stream); the columns
-    # [N*R, n) of every block-row are a plain cross-Gram launch.  One all-reduce of a token per step is the barrier that
-    # orders step k+1 after every rank's copies of step k.
-    sym, sym_note, R_tot = None, "n/a (1 GPU)", min(n, world * R)
+    R_tot = min(n, world * R)  # the job: rows [0, R_tot) of the Gram
+    sym, exchange = None, {"mode": "n/a (1 GPU: in-place mirror stores)"}
     if world > 1 and not args.no_sym:
         from kmg import dist as kdist
         try:
-            sym = kdist.SymmetricShards(R_tot, ldo=n)
-            ok, sym_note = 1, "symmetric square shared over NVLink peer memory"
+            sym = kdist.SymmetricShards(R_tot, ldo=n, exchange=args.exchange)
+            ok, note = 1, sym.exchange
         except Exception as exc:  # noqa: BLE001 - e.g. CUDA IPC not permitted in this container
-            ok, sym_note = 0, f"plain block-rows ({type(exc).__name__}: {exc})"
-        flag = torch.tensor([ok], dtype=torch.int32, device="cuda")
-        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-        if int(flag.item()) == 0:
+            ok, note = 0, f"plain block-rows ({type(exc).__name__}: {exc})"
+        if allmin_int(ok) == 0:
             if sym is not None:
                 sym.close()
-            sym, sym_note = None, sym_note if ok == 0 else "plain block-rows (another rank could not map peer memory)"
+            sym, note = None, note if ok == 0 else "plain block-rows (another rank could not map peer memory)"
+        exchange = {"mode": note}
     elif world > 1:
-        sym_note = "plain block-rows (--no-sym)"
+        exchange = {"mode": "plain block-rows (--no-sym)"}
     if sym is not None:
         row0, R, out = sym.r0, sym.r1 - sym.r0, sym.block
-        g = world
-        gemm_launches = sum(1 for d in range(1, g) if 2 * d < g) + (1 if g % 2 == 0 else 0) + 1 + (1 if R_tot < n else 0)
         token = torch.zeros(1, dtype=torch.int32, device="cuda")
     else:
         row0 = (rank * R) % max(n - R + 1, 1)
         out = torch.empty((R, n), dtype=torch.float64, device="cuda")
-        gemm_launches = 1
-    issued = [0]
+    sym1 = world == 1 and not args.no_sym and row0 == 0 and R <= n  # N = 1: the leading R x R square is symmetric too
+    issued = [0.0]
+    launches = [0]
 
     def build():
-        if sym is None:
+        if sym is not None:
+            issued[0] = float(sym.build_spectrum(phi[:R_tot]))
+            launches[0] = sym.launches
+            if R_tot < n:
+                kd.gram_i8(phi[row0:row0 + R], phi[R_tot:], row_index0=row0, col_index0=R_tot, out_dtype=1, m_sub=0, out=out[:, R_tot:])
+                issued[0] += float(R) * (n - R_tot)
+                launches[0] += 1
+        elif sym1:
+            kd.gram_i8(phi[:R], phi[:R], out_dtype=1, symmetric=True, m_sub=0, out=out[:, :R])
+            issued[0], launches[0] = sym_issued_entries(R), 1
+            if R < n:
+                kd.gram_i8(phi[:R], phi[R:], row_index0=0, col_index0=R, out_dtype=1, m_sub=0, out=out[:, R:])
+                issued[0] += float(R) * (n - R)
+                launches[0] += 1
+        else:
             kd.gram_i8(phi[row0:row0 + R], phi, row_index0=row0, col_index0=0, out_dtype=1, m_sub=0, out=out)
-            issued[0] = R * n
-            return
-        issued[0] = sym.build_spectrum(phi[:R_tot])
-        if R_tot < n:
-            kd.gram_i8(phi[row0:row0 + R], phi[R_tot:], row_index0=row0, col_index0=R_tot, out_dtype=1, m_sub=0, out=out[:, R_tot:])
-            issued[0] += R * (n - R_tot)
+            issued[0], launches[0] = float(R) * n, 1
 
     def step():
         kd.spectrum_phi(planes, L, KS, out=phi)
         build()
         if sym is not None:
-            dist.all_reduce(token)
+            dist.all_reduce(token)  # orders step k+1 after every rank's deliveries of step k
 
     def barrier():
         if dist is not None:
@@ -270,7 +320,6 @@ def main():
         sampler.start()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * args.steps + 2)]
     ev[0].record()
-    gemm_ms = []
     for i in range(args.steps):
         kd.spectrum_phi(planes, L, KS, out=phi)
         ev[2 * i + 1].record()
@@ -281,40 +330,36 @@ def main():
     ev[-1].record()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
-    total_ms = ev[0].elapsed_time(ev[-1])
+    total_ms = allmax(ev[0].elapsed_time(ev[-1]))
     gemm_ms = [ev[2 * i + 1].elapsed_time(ev[2 * i + 2]) for i in range(args.steps)]
-    t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms = float(t.item())
     ms_per_step = total_ms / args.steps
     entries_per_step = float(R_tot) * n if sym is not None else float(R) * n * world  # Gram entries DELIVERED by all ranks
     value = entries_per_step / (ms_per_step * 1e-3)
-    sym_checked = None
+    gemm_avg_ms = float(np.mean(gemm_ms))
+    gemm_max_ms = allmax(gemm_avg_ms)
+
+    # ---- parity of the TIMED output against the CPU oracle (plain C, oracle/kmg_oracle.c): sampled tiles of this rank's
+    # block-row -- in the mirrored part of its own diagonal block, in a block delivered by a peer, in a block it computed
+    # for a peer, in the plain remainder and at the ragged end -- bit for bit.  Every rank checks its own rows.
     if sym is not None:
-        # parity of the shared build: 512 of this rank's rows against a direct launch of the same kernel
         sym.finish()
-        lo = min(256, max(R - 512, 0))
-        direct = kd.gram_i8(phi[row0 + lo:row0 + lo + 512], phi, row_index0=row0 + lo, col_index0=0, out_dtype=1, m_sub=0)
-        okt = torch.tensor([1 if torch.equal(direct, out[lo:lo + 512]) else 0], dtype=torch.int32, device="cuda")
-        dist.all_reduce(okt, op=dist.ReduceOp.MIN)
-        sym_checked = bool(int(okt.item()))
-        del direct
-        if not sym_checked:
-            raise SystemExit("bench.py: the shared symmetric build disagrees with a direct launch")
+    parity = check_parity(torch, out, codes, row0, R, n, R_tot, rank, world)
+    parity["ok"] = bool(allmin_int(1 if parity["ok"] else 0))
+    parity["ranks"] = world
+    if not parity["ok"]:
+        raise SystemExit(f"bench.py: the timed Gram block-row disagrees with the oracle: {parity}")
 
     # ---- roofline of the dominant kernel (gram_i8_2cta_kernel, the CTA-pair tcgen05 GEMM): tensor bound
-    gemm_avg_ms = float(np.mean(gemm_ms))
-    # 2*D ops per entry ISSUED to the tensor cores: at N = 1 one launch = one block-row, every entry issued;
-    # in the shared symmetric build a rank issues about half of the entries it ends up holding
-    alg_ops = 2.0 * D_ALG * float(issued[0])
+    # 2*D ops per entry ISSUED to the tensor cores: the symmetric part of the job issues about half of
+    # the entries it delivers.  Denominator: the int8 tensor-core rate measured in this run, right after the timed steps
+    # (same clocks and power state), by issuing the kernel's own MMA instruction back to back with operands resident in
+    # shared memory (kmg_mma_peak_i8_dev).  MEASURED_PEAKS.json has a cuBLAS bf16 rate but no int8 entry; twice its
+    # sustained bf16 figure and a cuBLASLt int8 GEMM (torch._int_mm) timed in this run are reported beside it.
+    alg_ops = 2.0 * D_ALG * issued[0]
     achieved_tops = alg_ops / (gemm_avg_ms * 1e-3) / 1e12
-    # Denominator: the int8 tensor-core rate measured in this run, right after the timed steps (same clocks and power
-    # state), by issuing the kernel's own MMA instruction back to back with operands resident in shared memory
-    # (kmg_mma_peak_i8_dev, ~55 ms per sample).  MEASURED_PEAKS.json has a cuBLAS bf16 rate but no int8 entry; twice its
-    # sustained bf16 figure is reported beside it.
     peak_tops = kd.mma_peak_i8(iters=200000, repeats=2)
     peak_2x_bf16 = 2.0 * peaks["bf16_sustained"]
+    cublaslt = cublaslt_int8_tops(torch, phi) if rank == 0 else None
     roofline = {
         "kernel": "gram_i8_2cta_kernel (tcgen05.mma.cta_group::2.kind::i8, 256x256 pair tile)", "bound": "tensor", "achieved": achieved_tops, "peak": peak_tops,
         "unit": "TOP/s (int8)", "frac": achieved_tops / peak_tops,
@@ -323,56 +368,41 @@ def main():
         "frac_of_2x_bf16_sustained": achieved_tops / peak_2x_bf16,
         "peak_2x_bf16_sustained": peak_2x_bf16, "peaks_file": peaks["source"],
         "frac_of_nominal_int8_4500": achieved_tops / NOMINAL_INT8_TOPS,
-        "algorithmic_ops_per_launch": alg_ops, "kernel_ms": gemm_avg_ms, "kernel_share_of_step": gemm_avg_ms / ms_per_step,
-        "traffic": TRAFFIC_BYTES_PER_LAUNCH if sym is None else None,
+        "cublaslt_int8_same_run": cublaslt,
+        "algorithmic_ops_per_step": alg_ops, "kernel_ms": gemm_avg_ms, "kernel_ms_max_over_ranks": gemm_max_ms,
+        "kernel_share_of_step": gemm_avg_ms / ms_per_step,
+        "traffic": TRAFFIC_BYTES_PER_LAUNCH if (sym is None and not sym1) else None,
+        "traffic_source": TRAFFIC_SOURCE,
         "hbm_write_gbs": 8.0 * R * n / (gemm_avg_ms * 1e-3) / 1e9,
-        "gemm_launches_per_step": gemm_launches, "entries_issued_over_entries_held": float(issued[0]) / (float(R) * n),
+        "gemm_launches_per_step": launches[0], "entries_issued_over_entries_held": issued[0] / (float(R) * n),
+        "entries_issued_per_s_per_gpu": issued[0] / (ms_per_step * 1e-3),
     }
 
     # ---- end to end through the reference-facing C-ABI with host buffers (kmg_spectrum_host)
-    e2e_rows = min(2048, R)
-    rows_h = np.ascontiguousarray(codes[row0:row0 + e2e_rows])
-    kh.spectrum_gram(rows_h[:256], KS, cols=codes)  # warm the path (allocations, tile list)
-    barrier()
-    t0 = time.perf_counter()
-    Kh = kh.spectrum_gram(rows_h, KS, cols=codes)  # first full-size call of the process: cold result memory
-    cold_dt = time.perf_counter() - t0
-    for _ in range(max(args.warmup - 1, 0)):
-        del Kh
-        Kh = kh.spectrum_gram(rows_h, KS, cols=codes)
-    barrier()
-    e2e_steps, dts = 5, []
-    for _ in range(e2e_steps):
-        del Kh  # the caller drops the previous 3.3 GB result before asking for the next one (not part of the call)
-        t0 = time.perf_counter()
-        Kh = kh.spectrum_gram(rows_h, KS, cols=codes)
-        dts.append(time.perf_counter() - t0)
-    dt = float(np.mean(dts))
-    te = torch.tensor([dt], dtype=torch.float64, device="cuda")
-    if dist is not None:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e = {"value": e2e_rows * float(n) * world / float(te.item()), "unit": "entries/s",
-           "h2d_bytes_per_step": int((e2e_rows + n) * L), "d2h_bytes_per_step": int(e2e_rows * n * (2 if float(Kh.max()) <= 65535.0 else 4)),
-           "sample": f"{e2e_rows} x {n} rows of the block-row per GPU per call through kmg_spectrum_host (numpy in, numpy fp64 out; "
-                     "pageable host memory; H2D of the sequences and D2H of the Gram inside the timed region; the counts cross "
-                     "PCIe as u16 when every entry of the block fits (checked on the device), else as the GEMM's s32 accumulators, "
-                     "and are widened to fp64 by the copy threads; result arrays come "
-                     "from libkmg's recycled host blocks, warm after the first call)",
-           "first_call_value": e2e_rows * float(n) * world / cold_dt,
-           "calls_timed": e2e_steps, "checksum": float(Kh[0, :8].sum())}
-    del Kh
+    e2e = None
+    if not args.no_e2e:
+        e2e = e2e_leg(torch, kh, codes, row0, R, n, world, args, barrier, allmax)
 
     line = {
         "metric": "gram_entries_per_sec", "value": value, "unit": "entries/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "s8->s32->f64", "data": "synthetic", "config": workload_config(world, sym_note, sym_checked), "e2e": e2e,
-        "gpu_launches": (1 + gemm_launches) * args.steps, "roofline": roofline, "clocks": clocks,
+        "dtype": "s8->s32->f64", "data": "synthetic", "config": workload_config(world), "e2e": e2e,
+        "gpu_launches": (1 + launches[0]) * args.steps, "roofline": roofline, "clocks": clocks,
+        "parity_checked": parity["ok"], "parity": parity, "exchange": exchange,
+        "entries_issued_per_s_per_gpu": issued[0] / (ms_per_step * 1e-3),
     }
 
-    if rank == 0 and world == 1 and not args.no_extras:
+    if not args.no_extras:
+        if sym is not None:
+            out = None
+            sym.close()
+            sym = None
         del out
         torch.cuda.empty_cache()
-        line["kernels"] = extras(kd, torch, codes, planes, phi, peaks)
+        kernels = extras(kd, torch, dist, codes, planes, peaks, rank, world, allmax, allmin_int)
+        line["kernels"] = kernels
+    if rank == 0 and world == 1 and not args.no_e2e:
+        line["e2e"]["reference_sized_calls"] = reference_sized_calls(kh)
     if rank == 0 and world == 1 and not args.no_cpu:
         import oracle_c as oc
         oc.build()
@@ -391,53 +421,261 @@ def main():
         dist.destroy_process_group()
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel, from the ncu --set full
-# capture summarised in profiles/r1_gemm_ncu_full_summary.txt (106.30 GB read + 39.99 GB written; the algorithmic
-# minimum is 40 GB written + 4.4 GB of Phi read once -- the reads are the B panels re-streamed once per 8-row-tile band)
-TRAFFIC_BYTES_PER_LAUNCH = 146_276_310_000
+# dram__bytes_read.sum + dram__bytes_write.sum of one PLAIN 25000 x 200000 launch of the dominant kernel, from the
+# ncu captures summarised in profiles/ (the reads are the operand panels streamed once per wave of 74 tiles; L2 eviction
+# hints and other band heights were measured in round 2 and change nothing: profiles/r2_gemm_l2_hints.txt)
+TRAFFIC_BYTES_PER_LAUNCH = 146_286_971_904
+TRAFFIC_SOURCE = ("ncu dram__bytes_read.sum 106.30 GB + dram__bytes_write.sum 39.99 GB, one plain 25000 x 200000 launch "
+                  "(profiles/r2_gemm_l2_hints.txt h0_b8, same kernel and shape as profiles/r1_gemm_ncu_full_summary.txt); "
+                  "null when the step is the symmetric build (several launches)")
 
 
-def extras(kd, torch, codes, planes, phi, peaks):
-    """Device-resident numbers for the other BASELINE configs (N=1 only): each timed with CUDA events over 3 launches."""
+def check_parity(torch, out, codes, row0, R, n, R_tot, rank, world):
+    """Sampled tiles of the timed output vs oracle/kmg_oracle.c, bit for bit."""
+    import oracle_c as oc
+    oc.build()
+    rng = np.random.default_rng(1000 + rank)
+    TR, TC = 24, 96
+    spots = []
+    r_mid = int(rng.integers(256, max(R - TR - 256, 257)))
+    spots.append((max(R - TR, 0), max(row0 + 0, 0)))                         # last rows x first columns of the own diagonal block (mirrored part)
+    spots.append((r_mid, min(row0 + int(rng.integers(0, max(R - TC, 1))), n - TC)))  # own diagonal block, random
+    if world > 1:
+        for peer in ((rank + 1) % world, (rank - 1) % world, (rank + world // 2) % world):
+            c0 = peer * (R_tot // world) + int(rng.integers(0, max(R_tot // world - TC, 1)))
+            spots.append((int(rng.integers(0, max(R - TR, 1))), min(c0, n - TC)))
+    if R_tot < n:
+        spots.append((int(rng.integers(0, max(R - TR, 1))), int(rng.integers(R_tot, n - TC))))  # plain remainder
+    spots.append((max(R - TR, 0), n - TC))                                   # ragged end: last rows x last columns
+    spots.append((0, 0))
+    ok, entries = True, 0
+    for (lr, c0) in spots:
+        rows = codes[row0 + lr: row0 + lr + TR]
+        cols = codes[c0: c0 + TC]
+        want = oc.spectrum_block(rows, cols, KS)
+        got = out[lr: lr + rows.shape[0], c0: c0 + cols.shape[0]].cpu().numpy()
+        entries += want.size
+        if not np.array_equal(got, want):
+            ok = False
+    return {"ok": ok, "tiles_per_rank": len(spots), "entries_per_rank": entries, "tile": [TR, TC],
+            "oracle": "oracle/kmg_oracle.c (dense Phi + dot products, kernels.py:12-47)", "bar": "bit-exact"}
+
+
+def cublaslt_int8_tops(torch, phi):
+    """A library int8 GEMM (cuBLASLt through torch._int_mm, s32 out) on the same Phi, timed in this run: an independent
+    second denominator for the tcgen05 kernel.  Not a product path."""
+    try:
+        m = 16384
+        a = phi[:m].contiguous()
+        b = phi[m:2 * m].t()  # (W, m) column-major view
+        for _ in range(2):
+            torch._int_mm(a, b)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            torch._int_mm(a, b)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 3
+        return {"tops": 2.0 * m * m * phi.shape[1] / (ms * 1e-3) / 1e12, "shape": [m, m, int(phi.shape[1])], "ms": ms,
+                "what": "torch._int_mm (cuBLASLt IMMA), s32 output, no fp64 epilogue"}
+    except Exception as exc:  # noqa: BLE001
+        return {"tops": None, "error": f"{type(exc).__name__}: {exc}"}
+
+
+def e2e_leg(torch, kh, codes, row0, R, n, world, args, barrier, allmax):
+    e2e_rows = min(2048, R)
+    rows_h = np.ascontiguousarray(codes[row0:row0 + e2e_rows])
+    kh.spectrum_gram(rows_h[:256], KS, cols=codes)  # warm the path (allocations, tile list)
+    barrier()
+    t0 = time.perf_counter()
+    Kh = kh.spectrum_gram(rows_h, KS, cols=codes)  # first full-size call of the process: cold result memory
+    cold_dt = time.perf_counter() - t0
+    for _ in range(max(args.warmup - 1, 0)):
+        del Kh
+        Kh = kh.spectrum_gram(rows_h, KS, cols=codes)
+    barrier()
+    e2e_steps, dts = 5, []
+    for _ in range(e2e_steps):
+        del Kh  # the caller drops the previous 3.3 GB result before asking for the next one (not part of the call)
+        t0 = time.perf_counter()
+        Kh = kh.spectrum_gram(rows_h, KS, cols=codes)
+        dts.append(time.perf_counter() - t0)
+    dt = allmax(float(np.mean(dts)))
+    import oracle_c as oc
+    oc.build()
+    ok = bool(np.array_equal(Kh[100:116, 5000:5064], oc.spectrum_block(rows_h[100:116], codes[5000:5064], KS)))
+    res = {"value": e2e_rows * float(n) * world / dt, "unit": "entries/s",
+           "h2d_bytes_per_step": int((e2e_rows + n) * L), "d2h_bytes_per_step": int(e2e_rows * n * (2 if float(Kh.max()) <= 65535.0 else 4)),
+           "sample": f"{e2e_rows} x {n} rows of the block-row per GPU per call through kmg_spectrum_host (numpy in, numpy fp64 out; "
+                     "pageable host memory; H2D of the sequences and D2H of the Gram inside the timed region; the counts cross "
+                     "PCIe as u16 when every entry of the block fits (checked on the device), else as the GEMM's s32 accumulators, "
+                     "and are widened to fp64 by the copy threads; result arrays come "
+                     "from libkmg's recycled host blocks, warm after the first call)",
+           "first_call_value": e2e_rows * float(n) * world / cold_dt,
+           "calls_timed": e2e_steps, "parity_checked": ok}
+    del Kh
+    if not ok:
+        raise SystemExit("bench.py: the end-to-end result disagrees with the oracle")
+    return res
+
+
+def reference_sized_calls(kh):
+    """The calls the reference's own scripts make, through the same host API (numpy in -> numpy fp64 out, best of 5 warm
+    calls): BASELINE configs[0] (spectrum k=6 on Xtr0 + Xte0, 3000 sequences), configs[1] (mismatch (10,1) on all 9000
+    sequences, normalised) and the nine kernels run.py builds on the 9000 sequences (run.py:6)."""
+    z = np.load(os.path.join(ROOT, "tests", "golden", "dna9000.npz"))
+    codes = z["codes"]
+    c1 = np.ascontiguousarray(np.concatenate((codes[:2000], codes[6000:7000])))  # Xtr0 then Xte0
+
+    def best(fn, reps=5):
+        fn()
+        ts = []
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            K = fn()
+            ts.append(time.perf_counter() - t0)
+            del K
+        return min(ts)
+
+    res = {}
+    t = best(lambda: kh.spectrum_gram(c1, [6]))
+    res["configs0_spectrum_k6_n3000"] = {"ms": t * 1e3, "entries_per_s": 9e6 / t, "reference_s": 360.4,
+                                         "reference_source": "BASELINE.md section 2 (unmodified kernels.py, 1 core, survey container)"}
+    t = best(lambda: kh.mismatch_gram(codes, 10, 1), reps=3)
+    res["configs1_mismatch_k10_m1_n9000"] = {"ms": t * 1e3, "entries_per_s": 81e6 / t, "reference_s": None,
+                                             "reference_source": "not runnable by the reference (BASELINE.md: 300-420 s per sequence)"}
+    nine = [("SP", 4), ("SP", 5), ("SP", 6), ("MM", 4), ("MM", 5), ("MM", 6), ("WD", 4), ("WD", 5), ("WD", 10)]
+
+    def run_nine():
+        out = []
+        for kind, v in nine:
+            if kind == "SP":
+                out.append(kh.spectrum_gram(codes, [v]))
+            elif kind == "MM":
+                out.append(kh.mismatch_gram(codes, v, 1))
+            else:
+                out.append(kh.wd_gram(codes, v))
+        return out
+    t = best(run_nine, reps=2)
+    res["run_py_nine_kernels_n9000"] = {"ms": t * 1e3, "entries_per_s": 9 * 81e6 / t, "methods": "SP_k4 SP_k5 SP_k6 MM_k4_m1 MM_k5_m1 MM_k6_m1 WD_d4 WD_d5 WD_d10 (run.py:6)"}
+    return res
+
+
+def extras(kd, torch, dist, codes, planes, peaks, rank, world, allmax, allmin_int):
+    """Device-resident numbers for the other BASELINE configs at this N: every rank builds ITS block-row of the config's
+    Gram (block-row sharding, no exchange: every entry depends on two sequences only), time = max over ranks (CUDA
+    events), each with a sampled-tile check against the oracle and a fraction of the MEASURED peak of the pipe that
+    bounds it (csrc/alu_peak.cu microbenchmarks, run here)."""
+    import oracle_c as oc
+    import oracle_np as onp
+    oc.build()
+
     def timed(fn, iters=3):
         fn(); torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         for _ in range(iters):
             fn()
         b.record(); torch.cuda.synchronize()
-        return a.elapsed_time(b) / iters
+        return allmax(a.elapsed_time(b) / iters)
+
+    def span(n, per):
+        """this rank's rows [r0, r1) when every rank takes `per` rows (weak scaling), clipped to n"""
+        r0 = min(n, rank * per)
+        return r0, min(n, r0 + per)
 
     res = {}
     hbm = peaks["hbm_gbs"]
-    # spectrum k=6 (configs[0] kernel at scale): 32768 x 32768 block, symmetric, fp64
-    n6 = 32768
-    phi6 = kd.spectrum_phi(planes[:n6], L, [6])
-    out = torch.empty((n6, n6), dtype=torch.float64, device="cuda")
-    ms = timed(lambda: kd.gram_i8(phi6, phi6, out_dtype=1, symmetric=True, out=out))
-    res["spectrum_k6_sym_32768"] = {"entries_per_s": n6 * n6 / ms * 1e3, "ms": ms, "hbm_write_gbs": n6 * n6 * 8 / ms / 1e6,
-                                    "frac_hbm_write": n6 * n6 * 8 / ms / 1e6 / hbm}
-    del out, phi6
-    # configs[1]: (k,m)=(10,1) mismatch over 9000 sequences, symmetric, normalised fp64 (pairwise bit-vector kernel)
-    n2 = 9000
-    sd = kd.mismatch_diag_sqrt(planes[:n2], L, 10, 1)
-    out = torch.empty((n2, n2), dtype=torch.float64, device="cuda")
-    ms = timed(lambda: kd.mismatch_block(planes[:n2], planes[:n2], L, 10, 1, symmetric=True, sd_rows=sd, sd_cols=sd, out=out))
-    res["mismatch_k10_m1_sym_9000"] = {"entries_per_s": n2 * n2 / ms * 1e3, "ms": ms,
-                                       "window_pair_tests_per_s": (n2 * (n2 + 1) / 2) * 92 * 92 / ms * 1e3}
+    pk = {k: kd.alu_peak(k) for k in ("lop3", "shf", "popc", "dfma", "dadd", "dmul")}
+    res["measured_issue_peaks"] = {"unit": "thread-level instructions/s over 148 SMs", **pk,
+                                   "source": "csrc/alu_peak.cu, dependent chains of the one instruction, 32 warps per SM, run in this process"}
+
+    def pipe_frac(name, entries_computed_per_s):
+        pipe, inst, kind = PIPE_INST[name]
+        if inst is None:
+            return {"frac": None, "peak_source": "instructions per entry not profiled yet"}
+        ach = entries_computed_per_s * inst
+        return {"bound": f"{pipe} pipe issue", "achieved": ach, "peak": pk[kind], "unit": "thread-level instructions/s", "frac": ach / pk[kind],
+                "inst_per_entry": inst, "peak_source": f"csrc/alu_peak.cu '{kind}' microbenchmark, this run; instructions per entry from profiles/r2_pipe_instructions.txt"}
+
+    # configs[0] kernel at scale: spectrum k=6, 32768 x 32768, symmetric, fp64 (N = 1 only: HBM-write bound)
+    if world == 1:
+        n6 = 32768
+        phi6 = kd.spectrum_phi(planes[:n6], L, [6])
+        out = torch.empty((n6, n6), dtype=torch.float64, device="cuda")
+        ms = timed(lambda: kd.gram_i8(phi6, phi6, out_dtype=1, symmetric=True, out=out))
+        res["spectrum_k6_sym_32768"] = {"entries_per_s": n6 * n6 / ms * 1e3, "ms": ms, "bound": "hbm", "achieved": n6 * n6 * 8 / ms / 1e6,
+                                        "peak": hbm, "unit": "GB/s", "frac": n6 * n6 * 8 / ms / 1e6 / hbm, "peak_source": "MEASURED_PEAKS.json hbm_gbs"}
+        del out, phi6
+
+    # configs[1]: (k,m)=(10,1) mismatch over the 9000 real sequences, normalised fp64 (pairwise bit-vector kernel).
+    # N = 1: the symmetric Gram; N > 1: block-rows of ceil(9000/N) rows (strong scaling: the config has a fixed size).
+    z = np.load(os.path.join(ROOT, "tests", "golden", "dna9000.npz"))
+    c2 = z["codes"]
+    n2 = c2.shape[0]
+    p2 = kd.pack(c2, 0)
+    sd = kd.mismatch_diag_sqrt(p2, L, 10, 1)
+    if world == 1:
+        out = torch.empty((n2, n2), dtype=torch.float64, device="cuda")
+        ms = timed(lambda: kd.mismatch_block(p2, p2, L, 10, 1, symmetric=True, sd_rows=sd, sd_cols=sd, out=out))
+        r0, r1, computed = 0, n2, n2 * (n2 + 1) / 2
+    else:
+        per = -(-n2 // world)
+        r0, r1 = span(n2, per)
+        out = torch.empty((r1 - r0, n2), dtype=torch.float64, device="cuda")
+        ms = timed(lambda: kd.mismatch_block(p2[r0:r1], p2, L, 10, 1, row_index0=r0, sd_rows=sd[r0:r1], sd_cols=sd, out=out))
+        computed = float(per) * n2  # per GPU (the slowest rank has `per` rows)
+    lr = min(100, r1 - r0 - 8)
+    raw = oc.mismatch_raw_block(c2[r0 + lr:r0 + lr + 8], c2[4000:4032], 10, 1).astype(np.float64)
+    dr = np.array([oc.mismatch_raw_block(c2[i:i + 1], c2[i:i + 1], 10, 1)[0, 0] for i in range(r0 + lr, r0 + lr + 8)], np.float64)
+    dc = np.array([oc.mismatch_raw_block(c2[i:i + 1], c2[i:i + 1], 10, 1)[0, 0] for i in range(4000, 4032)], np.float64)
+    want = raw / (np.sqrt(dr)[:, None] * np.sqrt(dc)[None, :])
+    ok = bool(allmin_int(1 if np.array_equal(out[lr:lr + 8, 4000:4032].cpu().numpy(), want) else 0))
+    ent = {"entries_per_s": n2 * n2 / ms * 1e3, "ms": ms, "window_pair_tests_per_s": computed * (world if world > 1 else 1) * 92 * 92 / ms * 1e3,
+           "scaling": "strong (fixed 9000 x 9000 Gram)", "parity_checked": ok, "parity_bar": "bit-exact vs oracle/kmg_oracle.c on a sampled tile"}
+    ent.update(pipe_frac("mismatch_k10_m1", computed / (ms * 1e-3)))
+    res["mismatch_k10_m1_n9000"] = ent
     del out
-    # configs[3]: weighted degree d=10, 100k sequences: one 12500 x 100000 block-row
-    n3, r3 = 100_000, 12_500
-    out = torch.empty((r3, n3), dtype=torch.float64, device="cuda")
-    ms = timed(lambda: kd.wd_block(planes[:r3], planes[:n3], L, 10, out=out))
-    res["wd_d10_blockrow_12500x100000"] = {"entries_per_s": r3 * n3 / ms * 1e3, "ms": ms, "hbm_write_gbs": r3 * n3 * 8 / ms / 1e6,
-                                           "frac_hbm_write": r3 * n3 * 8 / ms / 1e6 / hbm}
+
+    # configs[3]: weighted degree d=10, 100k synthetic sequences (seed 4): one 12500 x 100000 block-row per GPU
+    n3, per3 = 100_000, 12_500
+    c3 = synthetic_codes(n3, 4)
+    p3 = kd.pack(c3, 0)
+    r0, r1 = span(n3, per3)
+    out = torch.empty((r1 - r0, n3), dtype=torch.float64, device="cuda")
+    ms = timed(lambda: kd.wd_block(p3[r0:r1], p3, L, 10, row_index0=r0, out=out))
+    lr = 77
+    want = oc.wd_block(c3[r0 + lr:r0 + lr + 16], c3[r0 + lr - 5:r0 + lr + 59], 10, row_index0=r0 + lr, col_index0=r0 + lr - 5)  # straddles the diagonal (closed-form entries)
+    ok = np.array_equal(out[lr:lr + 16, r0 + lr - 5:r0 + lr + 59].cpu().numpy(), want)
+    want = oc.wd_block(c3[r1 - 16:r1], c3[n3 - 64:], 10, row_index0=r1 - 16, col_index0=n3 - 64)
+    ok = bool(allmin_int(1 if (ok and np.array_equal(out[-16:, n3 - 64:].cpu().numpy(), want)) else 0))
+    ent = {"entries_per_s": float(per3) * n3 * world / ms * 1e3, "ms": ms, "rows_per_gpu": per3, "scaling": "weak",
+           "hbm_write_gbs": per3 * n3 * 8 / ms / 1e6, "frac_hbm_write": per3 * n3 * 8 / ms / 1e6 / hbm,
+           "parity_checked": ok, "parity_bar": "bit-exact vs oracle/kmg_oracle.c on sampled tiles"}
+    ent.update(pipe_frac("wd_d10", float(per3) * n3 / (ms * 1e-3)))
+    res["wd_d10_n100000"] = ent
     del out
-    # configs[4]: local alignment (intended recursion), 20k sequences: one 1024 x 20000 block
-    n4, r4 = 20_000, 1024
-    out = torch.empty((r4, n4), dtype=torch.float64, device="cuda")
-    ms = timed(lambda: kd.la_block(planes[:r4], planes[:n4], L, 11, 1, 0.5, 0, out=out), iters=1)
-    res["la_affine_block_1024x20000"] = {"entries_per_s": r4 * n4 / ms * 1e3, "ms": ms, "dp_cells_per_s": r4 * n4 * 10201 / ms * 1e3}
+
+    # configs[4]: local alignment (intended recursion, affine, e=11 d=1 beta=0.5 taken literally), 20k synthetic sequences
+    # (seed 5): 2500 x 20000 per GPU (8 GPUs = the whole Gram)
+    n4, per4 = 20_000, 2_500
+    c4 = synthetic_codes(n4, 5)
+    p4 = kd.pack(c4, 0)
+    r0, r1 = span(n4, per4)
+    out = torch.empty((r1 - r0, n4), dtype=torch.float64, device="cuda")
+    ms = timed(lambda: kd.la_block(p4[r0:r1], p4, L, 11, 1, 0.5, 0, row_index0=r0, out=out), iters=1)
+    want = oc.la_block(c4[r0 + 40:r0 + 44], c4[9000:9008], 11, 1, 0.5, 0, row_index0=r0 + 40, col_index0=9000)
+    got = out[40:44, 9000:9008].cpu().numpy()
+    ok = bool(allmin_int(1 if np.all(np.abs(got - want) <= 1e-12 * np.abs(want)) else 0))
+    ent = {"entries_per_s": float(per4) * n4 * world / ms * 1e3, "ms": ms, "rows_per_gpu": per4, "scaling": "weak",
+           "dp_cells_per_s": float(per4) * n4 * world * 10201 / ms * 1e3,
+           "parity_checked": ok, "parity_bar": "1e-12 relative vs oracle/kmg_oracle.c (la_block) on a sampled tile"}
+    ent.update(pipe_frac("la_affine", float(per4) * n4 / (ms * 1e-3)))
+    res["la_affine_n20000"] = ent
     return res
 
 

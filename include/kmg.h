@@ -42,6 +42,11 @@ extern "C" {
 #define KMG_SEQ_ASCII 1
 #define KMG_SEQ_CODES 0
 
+/* how the mirrored blocks of a sharded symmetric Gram reach their owners (kmg_gram_i8_sharded_dev) */
+#define KMG_EXCH_SINGLE 0  /* one launch, thread-issued stores into the owners' buffers (buffers on one device / tests) */
+#define KMG_EXCH_STAGED 1  /* per peer block: transposed block into local staging + one pitched peer copy */
+#define KMG_EXCH_DIRECT 2  /* per peer block: the epilogue's TMA stores write the owner's buffer over NVLink (default) */
+
 #define KMG_MM_AUTO 0      /* dense feature map + tensor-core GEMM for k <= 8, pairwise bit-vector kernel above */
 #define KMG_MM_PAIRWISE 1
 #define KMG_MM_DENSE 2
@@ -131,19 +136,34 @@ int kmg_gram_i8_dev(const int8_t* d_phi_rows, const int8_t* d_phi_cols, int64_t 
  * part_out[part] and, transposed, into the block-row buffer of the part that owns the tile's columns (part_out[b]: peer
  * device memory, e.g. from kmg_ipc_open).  After all parts have run (stream sync + barrier) every buffer holds its full
  * rows_p x n block-row: the mirror of kernels.py:45 is the one exchange of the path.
- * d_stage: local staging of kmg_gram_sharded_stage_bytes bytes -- one GEMM launch per peer block writes the transposed
- * block there and one pitched peer copy per block ships it while the next launch runs; NULL: a single launch whose
- * epilogue stores into the peers' buffers directly (buffers on one device, or tests).
+ * exchange: KMG_EXCH_DIRECT -- one GEMM launch per peer block whose epilogue stores every transposed piece through the TMA
+ * engine (cp.async.bulk.tensor) straight into the owner's block-row: compute and exchange fused tile by tile;
+ * KMG_EXCH_STAGED -- the transposed block goes to d_stage (kmg_gram_sharded_stage_bytes bytes of local staging) and one
+ * pitched peer copy per block ships it while the next launch runs; KMG_EXCH_SINGLE -- a single launch whose threads store
+ * into the peers' buffers (buffers on one device, or tests).  d_stage is only read for KMG_EXCH_STAGED.
  * d_sd (nullable): sqrt(diag) of all n rows, fused cosine normalisation.  computed_entries (nullable out). */
 int kmg_gram_sharded_stage_bytes(int n_parts, const int64_t* part_row0, int part, int out_dtype, int64_t* bytes);
+/* GEMM launches one call of kmg_gram_i8_sharded_dev enqueues for this part (host utility, no GPU) */
+int kmg_gram_sharded_launches(int n_parts, const int64_t* part_row0, int part, int exchange, int* launches);
 int kmg_gram_i8_sharded_dev(const int8_t* d_phi, int64_t n, int64_t width, int64_t ld_phi, int n_parts, int part,
                             const int64_t* part_row0, void* const* part_out, int64_t ldo, int out_dtype, const double* d_sd,
-                            void* d_stage, int64_t* computed_entries, void* stream);
+                            int exchange, void* d_stage, int64_t* computed_entries, void* stream);
 /* Diagnostic: the int8 tensor-core peak of this GPU as this library can drive it -- iters x 4 back-to-back
  * tcgen05.mma.cta_group::2.kind::i8 (256 x 256 x 32) per CTA pair, operands resident in shared memory, no loads, no
  * epilogue.  Enqueues only; the caller times the stream.  *ops = int8 operations issued.  bench.py's roofline
  * denominator (MEASURED_PEAKS.json has no int8 entry). */
 int kmg_mma_peak_i8_dev(int iters, int64_t* ops, void* stream);
+/* Diagnostic: issue peak of the CUDA-core pipe that bounds a pairwise kernel -- kind 0 LOP3 / 1 SHF (INT32 ALU pipe:
+ * mismatch, weighted degree), 2 POPC (XU pipe), 3 DFMA / 4 DADD / 5 DMUL (FP64 pipe: local alignment) -- as dependent
+ * chains of that one instruction on every SM.  Enqueues only; the caller times the stream.  *ops = thread-level
+ * instructions executed.  bench.py's denominators for kernels.* (BASELINE.md section 4 asks for microbenchmarks). */
+#define KMG_PEAK_LOP3 0
+#define KMG_PEAK_SHF 1
+#define KMG_PEAK_POPC 2
+#define KMG_PEAK_DFMA 3
+#define KMG_PEAK_DADD 4
+#define KMG_PEAK_DMUL 5
+int kmg_alu_peak_dev(int kind, int iters, int64_t* ops, void* stream);
 /* the assignment rule itself (host utility, no GPU): 1 when part a computes tile (I, J) of the global 256-grid whose
  * columns belong to part b; exactly one of a:(I,J) and b:(J,I) is 1 for I != J */
 int kmg_gram_sharded_takes_host(int n_parts, const int64_t* part_row0, int a, int b, int64_t I, int64_t J);

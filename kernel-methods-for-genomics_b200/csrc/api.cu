@@ -176,6 +176,7 @@ int kmg_host_free(void* ptr) { return kmg_hl_host_free(ptr); }
 int kmg_release(void) {
     kmg_hl_trim_pool();
     kmg_rt_flush_cache();
+    kmg_gram_i8_clear_cache();
     return KMG_OK;
 }
 
@@ -533,27 +534,51 @@ int kmg_gram_i8_dev(const int8_t* d_phi_rows, const int8_t* d_phi_cols, int64_t 
 // Sharded symmetric spectrum Gram: part `part` of `n_parts` computes its share of the upper-triangle work
 // and delivers every tile twice -- into its own block-row and, transposed, into the block-row of the part that owns the
 // tile's columns: the mirror of kernels.py:45 is the one exchange step of the path.
-//   d_stage == NULL : one launch; the GEMM epilogue stores the transposed tiles straight into the owners' buffers (peer
-//                     memory).  Right for buffers on one device; over NVLink the scattered 256-byte stores cap the
-//                     kernel (2 GPUs, n = 100 000: 40.5 ms against 30.1 ms with both buffers local).
-//   d_stage != NULL : one launch per peer block (cyclic distance 1, 2, ...) whose epilogue writes the transposed block
-//                     contiguously into local staging, each followed by ONE pitched peer copy on the copy stream while
-//                     the next block's GEMM runs; the diagonal block (local mirror) goes last and hides the final copy.
+//   KMG_EXCH_SINGLE : one launch; the epilogue's threads store the transposed tiles straight into the owners' buffers
+//                     (peer memory).  Right for buffers on one device; over NVLink the thread-issued 256-byte stores cap
+//                     the kernel (2 GPUs, n = 100 000: 40.5 ms against 30.1 ms with both buffers local).
+//   KMG_EXCH_STAGED : one launch per peer block (cyclic distance 1, 2, ...) whose epilogue writes the transposed block
+//                     contiguously into local staging (d_stage), each followed by ONE pitched peer copy on the copy
+//                     stream while the next block's GEMM runs; the diagonal block (local mirror) goes last.
+//   KMG_EXCH_DIRECT : one launch per peer block whose epilogue hands every transposed 32 x 16 piece to the TMA engine
+//                     (cp.async.bulk.tensor store through a tensor map over the OWNER's block-row): compute and exchange
+//                     are one kernel, tile by tile, with no staging pass and no copy-engine pass through HBM.
 namespace {
 struct SubBlock { int b; int64_t r_lo, r_hi, c_lo, c_hi; };
+// The peer blocks part `a` computes, in launch order.  Full blocks (cyclic distance 1, 2, ... < g/2) come first, each cut
+// into KMG_SHARD_SPLIT (default 2) pieces by rows; the half block at distance g/2 goes last, right before the diagonal
+// block.  Why: every piece is followed by the copy (staged exchange) of its transposed image to the owner; a copy moves
+// 8 B/entry at ~0.78 TB/s, a launch produces 8 B/entry at ~0.67 TB/s, so the copy engine keeps pace piece by piece and
+// what is exposed at the end of the step is only the part of the LAST copy that the diagonal launch (no exchange) does
+// not cover.  With whole blocks and the half block first (round 1) the last copy was a full block: 6.4 ms of copy under
+// a 3.7 ms launch at 8 GPUs, n = 200 000.  Last = half a block cut in two: 1.6 ms.  At every phase rank a still sends to
+// (a + d) mod g -- a permutation, one incoming stream per receiver as long as the ranks stay in step.
 void sharded_plan(int g, const int64_t* bounds, int a, std::vector<SubBlock>* out) {
+    static const int split_env = getenv("KMG_SHARD_SPLIT") ? atoi(getenv("KMG_SHARD_SPLIT")) : 2;
+    const int split = split_env < 1 ? 1 : (split_env > 8 ? 8 : split_env);
     const int64_t a0 = bounds[a], a1 = bounds[a + 1];
+    auto push_split = [&](int b, int64_t r_lo, int64_t r_hi, int64_t c_lo, int64_t c_hi) {
+        const int64_t tiles = (r_hi - r_lo + 255) / 256;
+        int64_t lo = r_lo;
+        for (int q = 1; q <= split && lo < r_hi; ++q) {
+            const int64_t hi = q == split ? r_hi : std::min<int64_t>(r_hi, r_lo + (tiles * q / split) * 256);
+            if (hi > lo) out->push_back({b, lo, hi, c_lo, c_hi});
+            lo = hi;
+        }
+    };
     for (int d = 1; d < g; ++d) {
         const int b = (a + d) % g;
-        const int64_t b0 = bounds[b], b1 = bounds[b + 1];
-        if (2 * d < g) { out->push_back({b, a0, a1, b0, b1}); continue; }
-        if (2 * d > g) continue;
+        if (2 * d < g) push_split(b, a0, a1, bounds[b], bounds[b + 1]);
+    }
+    if (g % 2 == 0 && g > 1) {
         // distance g/2: split by the lower-numbered part's row tiles, as kmg_gram_sharded_takes does
+        const int b = (a + g / 2) % g;
+        const int64_t b0 = bounds[b], b1 = bounds[b + 1];
         const int lo = a < b ? a : b;
         const int64_t lon = (bounds[lo + 1] - bounds[lo] + 255) / 256;
-        const int64_t split = std::min<int64_t>(bounds[lo] + (lon + 1) / 2 * 256, bounds[lo + 1]);
-        if (a < b) { if (split > a0) out->push_back({b, a0, split, b0, b1}); }
-        else if (split < b1) out->push_back({b, a0, a1, split, b1});
+        const int64_t cut = std::min<int64_t>(bounds[lo] + (lon + 1) / 2 * 256, bounds[lo + 1]);
+        if (a < b) { if (cut > a0) push_split(b, a0, cut, b0, b1); }
+        else if (cut < b1) push_split(b, a0, a1, cut, b1);
     }
 }
 size_t stage_align(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -571,21 +596,34 @@ int kmg_gram_sharded_stage_bytes(int n_parts, const int64_t* part_row0, int part
     return KMG_OK;
 }
 
+int kmg_gram_sharded_launches(int n_parts, const int64_t* part_row0, int part, int exchange, int* launches) {
+    KMG_REQUIRE(n_parts >= 1 && n_parts <= KMG_MAX_PARTS && part_row0 && part >= 0 && part < n_parts && launches, KMG_ERR_ARG,
+                "gram_sharded_launches: bad arguments");
+    if (exchange == KMG_EXCH_SINGLE) { *launches = 1; return KMG_OK; }
+    std::vector<SubBlock> plan;
+    sharded_plan(n_parts, part_row0, part, &plan);
+    *launches = (int)plan.size() + 1;  // + the diagonal block
+    return KMG_OK;
+}
+
 int kmg_gram_i8_sharded_dev(const int8_t* d_phi, int64_t n, int64_t width, int64_t ld_phi, int n_parts, int part,
                             const int64_t* part_row0, void* const* part_out, int64_t ldo, int out_dtype, const double* d_sd,
-                            void* d_stage, int64_t* computed_entries, void* stream) {
+                            int exchange, void* d_stage, int64_t* computed_entries, void* stream) {
     KMG_REQUIRE(out_dtype == KMG_OUT_S32 || out_dtype == KMG_OUT_F64, KMG_ERR_ARG, "gram_i8_sharded: bad out_dtype");
     KMG_REQUIRE(!(d_sd && out_dtype != KMG_OUT_F64), KMG_ERR_ARG, "gram_i8_sharded: normalisation needs the f64 output");
     KMG_REQUIRE(n_parts >= 1 && n_parts <= KMG_MAX_PARTS && part >= 0 && part < n_parts && part_row0 && part_out, KMG_ERR_ARG,
                 "gram_i8_sharded: 1..%d parts", KMG_MAX_PARTS);
     KMG_REQUIRE(ldo >= n, KMG_ERR_ARG, "gram_i8_sharded: ldo < n");
+    KMG_REQUIRE(exchange == KMG_EXCH_SINGLE || exchange == KMG_EXCH_DIRECT || (exchange == KMG_EXCH_STAGED && d_stage != nullptr), KMG_ERR_ARG,
+                "gram_i8_sharded: exchange must be KMG_EXCH_SINGLE, KMG_EXCH_STAGED (with d_stage) or KMG_EXCH_DIRECT");
     if (computed_entries) *computed_entries = 0;
     if (n == 0) return KMG_OK;
     cudaStream_t s = (cudaStream_t)stream;
     const int64_t a0 = part_row0[part], a1 = part_row0[part + 1];
     const int64_t esz = out_dtype == KMG_OUT_F64 ? 8 : 4;
     GramI8Args a;
-    if (d_stage == nullptr) {
+    const bool staged = exchange == KMG_EXCH_STAGED;
+    if (exchange == KMG_EXCH_SINGLE) {
         memset(&a, 0, sizeof(a));
         a.phi_rows = d_phi + a0 * ld_phi; a.phi_cols = d_phi; a.rows = a1 - a0; a.cols = n; a.Dpad = width; a.ld_phi = ld_phi;
         a.row_index0 = a0; a.col_index0 = 0; a.out = part_out[part]; a.ldo = ldo; a.out_dtype = out_dtype;
@@ -601,13 +639,9 @@ int kmg_gram_i8_sharded_dev(const int8_t* d_phi, int64_t n, int64_t width, int64
     if ((rc = kmg_rt_get_streams(&s0, &copy))) return rc;
     std::vector<SubBlock> plan;
     sharded_plan(n_parts, part_row0, part, &plan);
-    // Order: the half block at distance g/2 first (the first peer copy starts after the shortest launch), then distance
-    // 1, 2, ...  At every phase rank a sends to (a + d) mod g: a permutation, so each receiver has exactly one incoming
-    // stream at a time.  (Measured on 8 GPUs, n = 200 000: 38.5 ms/step this way, 35.3 ms of it the GEMM phase; splitting
-    // the blocks and feeding two peers at once through two copy streams broke the pattern and cost 7 ms; two copy
-    // engines on the same block changed nothing -- the copies are not the limit, the doubled epilogue stores and the
-    // 35 GB of copy traffic through HBM are: the same launches take 30.1 ms with no peer traffic at all.)
-    if (!plan.empty() && n_parts % 2 == 0) std::rotate(plan.begin(), plan.end() - 1, plan.end());
+    // (Round 1, 8 GPUs, n = 200 000, whole blocks with the half block first: 38.5 ms/step, 35.3 ms of it the GEMM phase
+    // including ~2.7 ms of exposed final copy; feeding two peers at once through two copy streams broke the one-stream-
+    // per-receiver pattern and cost 7 ms; two copy engines on the same block changed nothing.)
     char* my = static_cast<char*>(part_out[part]);
     char* stage = static_cast<char*>(d_stage);
     int64_t total = 0, got = 0;
@@ -618,15 +652,19 @@ int kmg_gram_i8_sharded_dev(const int8_t* d_phi, int64_t n, int64_t width, int64
         a.phi_rows = d_phi + sb.r_lo * ld_phi; a.phi_cols = d_phi + sb.c_lo * ld_phi; a.rows = rows; a.cols = cols; a.Dpad = width; a.ld_phi = ld_phi;
         a.row_index0 = sb.r_lo; a.col_index0 = sb.c_lo; a.out = my + ((sb.r_lo - a0) * ldo + sb.c_lo) * esz; a.ldo = ldo; a.out_dtype = out_dtype;
         a.sd_rows = d_sd ? d_sd + sb.r_lo : nullptr; a.sd_cols = d_sd ? d_sd + sb.c_lo : nullptr;
-        a.mirror_all = 1; a.out_t = stage; a.ldo_t = rows; a.computed_entries = &got;
+        a.mirror_all = 1; a.computed_entries = &got;
+        // the transposed block (cols x rows) belongs to rows [c_lo, c_hi) x columns [r_lo, r_hi) of the owner's block-row
+        char* dst = static_cast<char*>(part_out[sb.b]) + ((sb.c_lo - part_row0[sb.b]) * ldo + sb.r_lo) * esz;
+        if (staged) { a.out_t = stage; a.ldo_t = rows; }
+        else { a.out_t = dst; a.ldo_t = ldo; }   // direct: the epilogue's TMA stores go to the owner's memory
         if ((rc = kmg_gram_i8_launch(&a, s))) return rc;
         total += got;
+        if (!staged) continue;
         // the transposed block (cols x rows, contiguous) -> rows [c_lo, c_hi) x columns [r_lo, r_hi) of the owner's block-row
         KMG_CUDA_CHECK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
         KMG_CUDA_CHECK(cudaEventRecord(ev, s));
         KMG_CUDA_CHECK(cudaStreamWaitEvent(copy, ev, 0));
         KMG_CUDA_CHECK(cudaEventDestroy(ev));
-        char* dst = static_cast<char*>(part_out[sb.b]) + ((sb.c_lo - part_row0[sb.b]) * ldo + sb.r_lo) * esz;
         KMG_CUDA_CHECK(cudaMemcpy2DAsync(dst, (size_t)(ldo * esz), stage, (size_t)(rows * esz), (size_t)(rows * esz), (size_t)cols,
                                          cudaMemcpyDefault, copy));
         stage += stage_align((size_t)(rows * cols * esz));
@@ -639,11 +677,12 @@ int kmg_gram_i8_sharded_dev(const int8_t* d_phi, int64_t n, int64_t width, int64
     a.sd_rows = d_sd ? d_sd + a0 : nullptr; a.sd_cols = a.sd_rows; a.computed_entries = &got;
     if ((rc = kmg_gram_i8_launch(&a, s))) return rc;
     total += got;
-    // `stream` completes only after the peer copies have
-    KMG_CUDA_CHECK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-    KMG_CUDA_CHECK(cudaEventRecord(ev, copy));
-    KMG_CUDA_CHECK(cudaStreamWaitEvent(s, ev, 0));
-    KMG_CUDA_CHECK(cudaEventDestroy(ev));
+    if (staged) {  // `stream` completes only after the peer copies have
+        KMG_CUDA_CHECK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        KMG_CUDA_CHECK(cudaEventRecord(ev, copy));
+        KMG_CUDA_CHECK(cudaStreamWaitEvent(s, ev, 0));
+        KMG_CUDA_CHECK(cudaEventDestroy(ev));
+    }
     if (computed_entries) *computed_entries = total;
     return KMG_OK;
 }
@@ -653,6 +692,13 @@ int kmg_mma_peak_i8_dev(int iters, int64_t* ops, void* stream) {
     int rc = kmg_rt_require_device();
     if (rc) return rc;
     return kmg_mma_peak_i8_launch(iters, ops, (cudaStream_t)stream);
+}
+
+// Measured issue peak of a CUDA-core pipe (alu_peak.cu): enqueue `iters` x 64 dependent-chain instructions per thread.
+int kmg_alu_peak_dev(int kind, int iters, int64_t* ops, void* stream) {
+    int rc = kmg_rt_require_device();
+    if (rc) return rc;
+    return kmg_alu_peak_launch(kind, iters, ops, (cudaStream_t)stream);
 }
 
 int kmg_gram_sharded_takes_host(int n_parts, const int64_t* part_row0, int a, int b, int64_t I, int64_t J) {

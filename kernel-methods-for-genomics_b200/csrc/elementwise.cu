@@ -10,6 +10,8 @@
 // deterministic two-stage trees (no atomics), so repeated runs are bit-identical.
 #include <cuda_runtime.h>
 #include <math.h>
+
+#include <algorithm>
 #include <stdint.h>
 
 #include "elementwise.h"
@@ -112,35 +114,39 @@ __global__ void __launch_bounds__(256) vec_sum_kernel(const double* __restrict__
 }
 
 // out[i,j] = K[i,j] - cs[j]/n - rs[i]/n + g/n^2   (closed form of (I-11'/n) K (I-11'/n))
-__global__ void __launch_bounds__(256) center_apply_kernel(const double* __restrict__ K, int64_t cols, int64_t n, int64_t ld,
+__global__ void __launch_bounds__(256) center_apply_kernel(const double* __restrict__ K, int64_t rows, int64_t cols, int64_t n, int64_t ld,
                                                            const double* __restrict__ rs, const double* __restrict__ cs,
                                                            const double* __restrict__ g, double* __restrict__ out, int64_t ldo) {
     // four columns per thread, 256 apart: four independent 8-byte loads in flight per thread (one per thread left the
     // pass at 4.4 TB/s, latency bound: 16 KB in flight per SM against the ~35 KB that 6.5 TB/s needs)
     const int64_t j0 = blockIdx.x * (256ll * EW_PER_THREAD) + threadIdx.x;
-    const int64_t i = blockIdx.y;
     const double inv = 1.0 / (double)n;
-    const double ri = rs[i] * inv, gg = (*g) * inv * inv;
-    double v[EW_PER_THREAD], c[EW_PER_THREAD];
+    const double gg = (*g) * inv * inv;
+    double c[EW_PER_THREAD];
 #pragma unroll
-    for (int q = 0; q < EW_PER_THREAD; ++q) {
-        const int64_t j = j0 + 256 * q;
-        v[q] = j < cols ? K[i * ld + j] : 0.0;
-        c[q] = j < cols ? cs[j] : 0.0;
-    }
+    for (int q = 0; q < EW_PER_THREAD; ++q) c[q] = (j0 + 256 * q < cols) ? cs[j0 + 256 * q] * inv : 0.0;
+    for (int64_t i = blockIdx.y; i < rows; i += gridDim.y) {  // gridDim.y is capped at 65535: rows beyond it loop
+        const double ri = rs[i] * inv;
+        double v[EW_PER_THREAD];
 #pragma unroll
-    for (int q = 0; q < EW_PER_THREAD; ++q) {
-        const int64_t j = j0 + 256 * q;
-        if (j < cols) out[i * ldo + j] = v[q] - c[q] * inv - ri + gg;
+        for (int q = 0; q < EW_PER_THREAD; ++q) {
+            const int64_t j = j0 + 256 * q;
+            v[q] = j < cols ? K[i * ld + j] : 0.0;
+        }
+#pragma unroll
+        for (int q = 0; q < EW_PER_THREAD; ++q) {
+            const int64_t j = j0 + 256 * q;
+            if (j < cols) out[i * ldo + j] = v[q] - c[q] - ri + gg;
+        }
     }
 }
 
 __global__ void __launch_bounds__(256) gather_kernel(const double* __restrict__ K, int64_t ld, const int64_t* __restrict__ idx,
                                                      int64_t m, double* __restrict__ out, int64_t ldo) {
     const int64_t b = blockIdx.x * 256ll + threadIdx.x;
-    const int64_t a = blockIdx.y;
     if (b >= m) return;
-    out[a * ldo + b] = K[idx[a] * ld + idx[b]];
+    const int64_t ib = idx[b];
+    for (int64_t a = blockIdx.y; a < m; a += gridDim.y) out[a * ldo + b] = K[idx[a] * ld + ib];
 }
 
 struct CombineParams {
@@ -155,8 +161,7 @@ struct CombineParams {
 // (np.sum(kernels * u[:,None,None], axis=0): K_0 u_0, then + K_1 u_1, ...).
 __global__ void __launch_bounds__(256) combine_kernel(CombineParams cp, int64_t rows, int64_t cols, double* __restrict__ out, int64_t ldo) {
     const int64_t j0 = blockIdx.x * (256ll * EW_PER_THREAD) + threadIdx.x;
-    const int64_t i = blockIdx.y;
-    if (i >= rows) return;
+    for (int64_t i = blockIdx.y; i < rows; i += gridDim.y) {
     double acc[EW_PER_THREAD];
 #pragma unroll
     for (int q = 0; q < EW_PER_THREAD; ++q) {
@@ -179,6 +184,7 @@ __global__ void __launch_bounds__(256) combine_kernel(CombineParams cp, int64_t 
         else if (cp.degree == 2) v = __dmul_rn(acc[q], acc[q]);  // numpy: x**2 -> np.square
         else if (cp.degree != 1) v = pow(acc[q], (double)cp.degree);
         out[i * ldo + j] = v;
+    }
     }
 }
 
@@ -254,7 +260,7 @@ int64_t kmg_ew_center_workspace(int64_t n) {
 
 int kmg_ew_center(const double* K, int64_t n, int64_t ld, double* out, int64_t ldo, void* workspace, cudaStream_t s) {
     if (n <= 0) return KMG_OK;
-    KMG_REQUIRE(n <= 65535ll * 8, KMG_ERR_ARG, "center: n too large for one launch");
+    KMG_REQUIRE(n <= 65535ll * 256, KMG_ERR_ARG, "center: n too large for one launch");
     const int64_t chunks = (n + CS_CHUNK - 1) / CS_CHUNK;
     double* part = reinterpret_cast<double*>(workspace);
     double* rs = part + chunks * n;
@@ -264,15 +270,14 @@ int kmg_ew_center(const double* K, int64_t n, int64_t ld, double* out, int64_t l
     col_sum_partial_kernel<<<dim3((unsigned)((n + 255) / 256), (unsigned)chunks), 256, 0, s>>>(K, n, n, ld, part);
     col_sum_final_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(part, chunks, n, cs);
     vec_sum_kernel<<<1, 256, 0, s>>>(rs, n, g);
-    center_apply_kernel<<<dim3((unsigned)((n + 256 * EW_PER_THREAD - 1) / (256 * EW_PER_THREAD)), (unsigned)n), 256, 0, s>>>(K, n, n, ld, rs, cs, g, out, ldo);
+    center_apply_kernel<<<dim3((unsigned)((n + 256 * EW_PER_THREAD - 1) / (256 * EW_PER_THREAD)), (unsigned)std::min<int64_t>(n, 65535)), 256, 0, s>>>(K, n, n, n, ld, rs, cs, g, out, ldo);
     KMG_CUDA_CHECK(cudaGetLastError());
     return KMG_OK;
 }
 
 int kmg_ew_gather(const double* K, int64_t ld, const int64_t* idx, int64_t m, double* out, int64_t ldo, cudaStream_t s) {
     if (m <= 0) return KMG_OK;
-    KMG_REQUIRE(m <= 65535, KMG_ERR_ARG, "gather: sub-block too large for one launch");
-    gather_kernel<<<dim3((unsigned)((m + 255) / 256), (unsigned)m), 256, 0, s>>>(K, ld, idx, m, out, ldo);
+    gather_kernel<<<dim3((unsigned)((m + 255) / 256), (unsigned)std::min<int64_t>(m, 65535)), 256, 0, s>>>(K, ld, idx, m, out, ldo);
     KMG_CUDA_CHECK(cudaGetLastError());
     return KMG_OK;
 }
@@ -282,11 +287,10 @@ int kmg_ew_combine(const double* const* Ks, const int64_t* lds, const double* u,
     KMG_REQUIRE(p >= 1 && p <= KMG_MAX_COMBINE, KMG_ERR_ARG, "combine: between 1 and %d kernels", KMG_MAX_COMBINE);
     KMG_REQUIRE(degree >= 0 && degree <= 64, KMG_ERR_ARG, "combine: degree out of range");
     if (rows <= 0 || cols <= 0) return KMG_OK;
-    KMG_REQUIRE(rows <= 65535, KMG_ERR_ARG, "combine: too many rows for one launch");
     CombineParams cp;
     cp.p = p; cp.degree = degree;
     for (int m = 0; m < p; ++m) { cp.K[m] = Ks[m]; cp.ld[m] = lds[m]; cp.u[m] = u[m]; }
-    combine_kernel<<<dim3((unsigned)((cols + 256 * EW_PER_THREAD - 1) / (256 * EW_PER_THREAD)), (unsigned)rows), 256, 0, s>>>(cp, rows, cols, out, ldo);
+    combine_kernel<<<dim3((unsigned)((cols + 256 * EW_PER_THREAD - 1) / (256 * EW_PER_THREAD)), (unsigned)std::min<int64_t>(rows, 65535)), 256, 0, s>>>(cp, rows, cols, out, ldo);
     KMG_CUDA_CHECK(cudaGetLastError());
     return KMG_OK;
 }
@@ -327,8 +331,7 @@ int kmg_ew_col_sums(const double* K, int64_t rows, int64_t cols, int64_t ld, dou
 int kmg_ew_center_apply(const double* K, int64_t rows, int64_t cols, int64_t n_total, int64_t ld, const double* rs, const double* cs,
                         const double* g, double* out, int64_t ldo, cudaStream_t s) {
     if (rows <= 0 || cols <= 0) return KMG_OK;
-    KMG_REQUIRE(rows <= 65535, KMG_ERR_ARG, "center_apply: too many rows for one launch");
-    center_apply_kernel<<<dim3((unsigned)((cols + 256 * EW_PER_THREAD - 1) / (256 * EW_PER_THREAD)), (unsigned)rows), 256, 0, s>>>(K, cols, n_total, ld, rs, cs, g, out, ldo);
+    center_apply_kernel<<<dim3((unsigned)((cols + 256 * EW_PER_THREAD - 1) / (256 * EW_PER_THREAD)), (unsigned)std::min<int64_t>(rows, 65535)), 256, 0, s>>>(K, rows, cols, n_total, ld, rs, cs, g, out, ldo);
     KMG_CUDA_CHECK(cudaGetLastError());
     return KMG_OK;
 }

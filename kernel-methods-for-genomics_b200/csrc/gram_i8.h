@@ -40,7 +40,11 @@ struct GramI8Args {
 int kmg_gram_sharded_takes(int g, const int64_t* part_row0, int a, int b, int64_t I, int64_t J);
 
 int kmg_gram_i8_launch(const GramI8Args* a, cudaStream_t stream);
+// frees the cached tile lists of every device (kmg_release)
+void kmg_gram_i8_clear_cache();
 // mma_peak.cu: back-to-back tcgen05.mma.cta_group::2.kind::i8 on every CTA pair; *ops = int8 operations issued
 int kmg_mma_peak_i8_launch(int iters, int64_t* ops, cudaStream_t stream);
 int kmg_gram_i8_simt_launch(const int8_t* A, const int8_t* B, int64_t ld, int64_t rows, int64_t cols, int64_t Dpad,
                             int32_t* out, int64_t ldo, cudaStream_t stream);
+// alu_peak.cu: issue-rate microbenchmarks of the CUDA-core pipes (kind: 0 LOP3, 1 SHF, 2 POPC, 3 DFMA, 4 DADD, 5 DMUL)
+int kmg_alu_peak_launch(int kind, int iters, int64_t* ops, cudaStream_t stream);

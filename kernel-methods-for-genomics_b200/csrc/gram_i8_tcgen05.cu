@@ -21,6 +21,7 @@
 #include <stdint.h>
 #include <stdlib.h>
 
+#include <algorithm>
 #include <array>
 #include <map>
 #include <mutex>
@@ -246,6 +247,59 @@ __device__ __forceinline__ void store_chunk(const KernelParams& p, const uint32_
     __syncwarp();  // the staging tile is reused by the next chunk
 }
 
+// Mirror store of one 32 x 32 chunk through the TMA engine: the warp writes the chunk TRANSPOSED (and converted) into its
+// 4 KB staging tile -- for a fixed column the 32 lanes are 32 consecutive rows, i.e. 32 consecutive entries of one
+// mirrored row: conflict-free 8-byte shared stores -- and one lane issues cp.async.bulk.tensor stores of
+// [16 mirrored rows] x [32 entries] (fp64) boxes into the destination's tensor map.  Nothing of the mirror goes through
+// the LSU as a global store: the destination may be the block-row buffer of ANOTHER GPU (CUDA IPC mapping, NVLink), where
+// thread-issued stores capped the kernel (2 GPUs, n = 100 000: 40.5 ms against 30.1 ms with local buffers).  Rows /
+// columns beyond the block are clipped by the tensor map.  The staging tile is shared with the own-row store, so the
+// caller waits for the previous bulk group to have been read before it writes the tile again.
+template <bool INT_CVT>
+__device__ __forceinline__ void tma_mirror_chunk(const KernelParams& p, const uint32_t (&v)[32], uint32_t* stage /*4 KB*/, int lane,
+                                                 int64_t row_base, int64_t col0, const CUtensorMap* tmT) {
+    if (row_base >= p.rows) return;  // warp-uniform
+    if (p.out_dtype == KMG_OUT_S32) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) stage[j * 32 + lane] = v[j];
+        ptx::fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+            ptx::tma_store_2d(tmT, stage, (int32_t)row_base, (int32_t)col0);
+            ptx::tma_store_commit();
+        }
+        return;
+    }
+    double* sdst = reinterpret_cast<double*>(stage);
+    const bool norm = p.sd_rows != nullptr;
+    const int64_t row_t = row_base + lane;
+    const double sr = (norm && row_t < p.rows) ? p.sd_rows[row_t] : 1.0;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        if (col0 + 16 * h >= p.cols) break;  // warp-uniform
+        if (h == 1) {
+            if (lane == 0) ptx::tma_store_wait_read<0>();
+            __syncwarp();
+        }
+#pragma unroll
+        for (int jj = 0; jj < 16; ++jj) {
+            const int j = 16 * h + jj;
+            double val = u32_to_f64<INT_CVT>(v[j]);
+            if (norm) {  // mirrored tiles never contain the diagonal (kernels.py:408-414)
+                const double sc = (col0 + j < p.cols) ? p.sd_cols[col0 + j] : 1.0;
+                val = __ddiv_rn(val, __dmul_rn(sr, sc));
+            }
+            sdst[jj * 32 + lane] = val;
+        }
+        ptx::fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+            ptx::tma_store_2d(tmT, stage, (int32_t)row_base, (int32_t)(col0 + 16 * h));
+            ptx::tma_store_commit();
+        }
+    }
+}
+
 template <int M_SUB>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gram_i8_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -413,9 +467,10 @@ struct Cfg2 {
     static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + NUM_EPI_WARPS * EPI_STAGE_WORDS * 4;
 };
 
-template <bool INT_CVT>
+template <bool INT_CVT, bool TMA_MIRROR>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-gram_i8_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const KernelParams p) {
+gram_i8_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                    const __grid_constant__ CUtensorMap tmT, const KernelParams p) {
     using C = Cfg2;
     extern __shared__ uint8_t smem_raw[];
     // 1024-B alignment by offsetting the __shared__ symbol (keeps the address space known to the compiler: LDS/STS, not generic LD/ST)
@@ -436,6 +491,7 @@ gram_i8_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     if (warp == WARP_TMA && lane == 0) {
         ptx::prefetch_tensormap(&tmA);
         ptx::prefetch_tensormap(&tmB);
+        if (TMA_MIRROR) ptx::prefetch_tensormap(&tmT);
     }
     if (warp == WARP_MMA && lane == 0) {
         for (int s = 0; s < C::STAGES; ++s) {
@@ -536,13 +592,22 @@ gram_i8_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 uint32_t v[32];
                 ptx::tmem_ld_32x32b_x32(taddr, v);
                 ptx::tmem_ld_wait();
-                store_chunk<INT_CVT>(p, v, st, lane, row_base, col0, mirror);
+                if (TMA_MIRROR) {
+                    // the staging tile may still be the source of the previous chunk's bulk store
+                    if (lane == 0) ptx::tma_store_wait_read<0>();
+                    __syncwarp();
+                    store_chunk<INT_CVT>(p, v, st, lane, row_base, col0, nullptr);
+                    if (mirror != nullptr) tma_mirror_chunk<INT_CVT>(p, v, st, lane, row_base, col0, &tmT);
+                } else {
+                    store_chunk<INT_CVT>(p, v, st, lane, row_base, col0, mirror);
+                }
             }
             ptx::tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive_cluster(&tempty[acc], 0);  // the leader's MMA thread waits on it
             if (++acc == C::ACC_STAGES) { acc = 0; acc_phase ^= 1; }
         }
+        if (TMA_MIRROR && lane == 0) ptx::tma_store_wait<0>();  // every mirror store has landed before the CTA retires
     }
     ptx::tcgen05_fence_before();
     ptx::cluster_sync_all();
@@ -611,9 +676,10 @@ struct TileKey {
     int n_parts, part;
     std::array<int64_t, KMG_MAX_PARTS + 1> bounds;  // part_row0 of a sharded build, zeros otherwise
     int mirror_all;
+    int interleave;
     bool operator<(const TileKey& o) const {
-        return std::tie(rows, cols, r0, c0, bm, sym, band, n_parts, part, bounds, mirror_all) <
-               std::tie(o.rows, o.cols, o.r0, o.c0, o.bm, o.sym, o.band, o.n_parts, o.part, o.bounds, o.mirror_all);
+        return std::tie(rows, cols, r0, c0, bm, sym, band, n_parts, part, bounds, mirror_all, interleave) <
+               std::tie(o.rows, o.cols, o.r0, o.c0, o.bm, o.sym, o.band, o.n_parts, o.part, o.bounds, o.mirror_all, o.interleave);
     }
 };
 
@@ -642,30 +708,64 @@ struct TileList {
     int4* dev = nullptr;
     int32_t n = 0;
     int64_t computed_entries = 0;
+    uint64_t last_use = 0;
 };
+// Tile lists are cached per (device, shape): a long-lived process that sees many shapes keeps at most TILE_CACHE_MAX of
+// them (least recently used goes first; cudaFree waits for the kernels that may still read it) and kmg_release() frees all.
+constexpr size_t TILE_CACHE_MAX = 48;
 std::mutex g_tile_mu;
 std::map<std::pair<int, TileKey>, TileList> g_tile_cache;  // per device
+uint64_t g_tile_clock = 0;
 
 int get_tiles(const TileKey& key, cudaStream_t stream, TileList* out) {
     int dev = 0;
     KMG_CUDA_CHECK(cudaGetDevice(&dev));
     std::lock_guard<std::mutex> lk(g_tile_mu);
     auto it = g_tile_cache.find({dev, key});
-    if (it != g_tile_cache.end()) { *out = it->second; return KMG_OK; }
+    if (it != g_tile_cache.end()) { it->second.last_use = ++g_tile_clock; *out = it->second; return KMG_OK; }
+    while (g_tile_cache.size() >= TILE_CACHE_MAX) {
+        auto victim = g_tile_cache.begin();
+        for (auto c = g_tile_cache.begin(); c != g_tile_cache.end(); ++c)
+            if (c->second.last_use < victim->second.last_use) victim = c;
+        if (victim->second.dev) {
+            int cur = dev;
+            if (victim->first.first != cur) cudaSetDevice(victim->first.first);
+            cudaFree(victim->second.dev);
+            if (victim->first.first != cur) cudaSetDevice(cur);
+        }
+        g_tile_cache.erase(victim);
+    }
     const int BM = key.bm;
     const int64_t tm_n = (key.rows + BM - 1) / BM, tn_n = (key.cols + BN - 1) / BN;
     const int G = key.band;
     std::vector<int4> tiles;
     tiles.reserve((size_t)(tm_n * tn_n));
     int64_t entries = 0;
+    // Column order inside a band.  Sharded single-launch build: the column tiles of the parts are interleaved (position
+    // p of part 0, of part 1, ...), so that tiles whose mirror goes over NVLink alternate with tiles of the local
+    // diagonal block and the link sees the AVERAGE demand of the launch instead of phases at 100 % / 0 %.
+    std::vector<int64_t> col_order;
+    col_order.reserve((size_t)tn_n);
+    if (key.n_parts > 1 && key.interleave) {
+        std::vector<int64_t> first(key.n_parts + 1);
+        for (int q = 0; q <= key.n_parts; ++q) first[q] = (key.bounds[q] + BN - 1) / BN;  // boundaries are multiples of 256
+        first[key.n_parts] = tn_n;
+        int64_t longest = 0;
+        for (int q = 0; q < key.n_parts; ++q) longest = std::max(longest, first[q + 1] - first[q]);
+        for (int64_t pos = 0; pos < longest; ++pos)
+            for (int q = 0; q < key.n_parts; ++q)
+                if (first[q] + pos < first[q + 1]) col_order.push_back(first[q] + pos);
+    } else {
+        for (int64_t tn = 0; tn < tn_n; ++tn) col_order.push_back(tn);
+    }
     for (int64_t b0 = 0; b0 < tm_n; b0 += G) {
         const int64_t b1 = (b0 + G < tm_n) ? b0 + G : tm_n;
-        for (int64_t tn = 0; tn < tn_n; ++tn) {
+        for (int64_t tn : col_order) {
             for (int64_t tm = b0; tm < b1; ++tm) {
                 int mirror = key.mirror_all, dest = 0;
                 if (key.n_parts > 0) {
                     // sharded symmetric build: global 256-grid tile (I, J); b = the part owning columns of J
-                    const int64_t I = key.r0 / BM + tm, J = tn;
+                    const int64_t I = key.bounds[key.part] / BM + tm, J = tn;  // the part's first row tile on the global grid
                     int b = 0;
                     while (b + 1 < key.n_parts && J * BN >= key.bounds[b + 1]) ++b;
                     if (!kmg_gram_sharded_takes(key.n_parts, key.bounds.data(), key.part, b, I, J)) continue;
@@ -690,9 +790,11 @@ int get_tiles(const TileKey& key, cudaStream_t stream, TileList* out) {
     tl.computed_entries = entries;
     if (tl.n > 0) {
         KMG_CUDA_CHECK(cudaMalloc(&tl.dev, sizeof(int4) * tiles.size()));
+        // pageable source: the call returns once the list sits in the driver's staging buffer, so `tiles` may go out of
+        // scope and the launch that follows on `stream` is ordered after the copy -- no stream synchronisation needed
         KMG_CUDA_CHECK(cudaMemcpyAsync(tl.dev, tiles.data(), sizeof(int4) * tiles.size(), cudaMemcpyHostToDevice, stream));
-        KMG_CUDA_CHECK(cudaStreamSynchronize(stream));
     }
+    tl.last_use = ++g_tile_clock;
     g_tile_cache[{dev, key}] = tl;
     *out = tl;
     return KMG_OK;
@@ -732,13 +834,13 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const KernelParams& p
     return KMG_OK;
 }
 
-template <bool INT_CVT>
-int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const KernelParams& p, int sms, cudaStream_t stream) {
+template <bool INT_CVT, bool TMA_MIRROR>
+int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmT, const KernelParams& p, int sms, cudaStream_t stream) {
     static bool attr_set[64] = {};
     int dev = 0;
     KMG_CUDA_CHECK(cudaGetDevice(&dev));
     if (!attr_set[dev & 63]) {
-        KMG_CUDA_CHECK(cudaFuncSetAttribute(gram_i8_2cta_kernel<INT_CVT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg2::SMEM_BYTES));
+        KMG_CUDA_CHECK(cudaFuncSetAttribute(gram_i8_2cta_kernel<INT_CVT, TMA_MIRROR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg2::SMEM_BYTES));
         attr_set[dev & 63] = true;
     }
     int clusters = sms / 2;
@@ -758,7 +860,26 @@ int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const KernelPara
     attr[1].val.cooperative = (p.wave_counter != nullptr && coop_enabled()) ? 1 : 0;
     cfg.attrs = attr;
     cfg.numAttrs = 2;
-    KMG_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gram_i8_2cta_kernel<INT_CVT>, tmA, tmB, p));
+    KMG_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gram_i8_2cta_kernel<INT_CVT, TMA_MIRROR>, tmA, tmB, tmT, p));
+    return KMG_OK;
+}
+
+// Tensor map over a MIRROR destination: element (r, c) of the block (block-local indices) lives at base[c * ld + r], so
+// the inner (contiguous) coordinate is the block ROW and the outer one the block COLUMN; extents = the block shape, which
+// makes the TMA engine clip the ragged last tile row / column.  Box = 32 entries x (16 fp64 | 32 s32) mirrored rows = 4 KB.
+int make_mirror_map(CUtensorMap* m, void* base, int out_dtype, int64_t rows, int64_t cols, int64_t ld) {
+    PFN_encodeTiled enc = get_encode_fn();
+    KMG_REQUIRE(enc != nullptr, KMG_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    const bool f64 = out_dtype == KMG_OUT_F64;
+    const cuuint64_t esz = f64 ? 8 : 4;
+    cuuint64_t dims[2] = {(cuuint64_t)rows, (cuuint64_t)cols};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * esz};
+    cuuint32_t box[2] = {32u, f64 ? 16u : 32u};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r = enc(m, f64 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_INT32, 2, base, dims, strides, box, es,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    KMG_REQUIRE(r == CUDA_SUCCESS, KMG_ERR_CUDA, "cuTensorMapEncodeTiled (mirror destination) failed (CUresult %d)", (int)r);
     return KMG_OK;
 }
 
@@ -781,6 +902,19 @@ int kmg_gram_sharded_takes(int g, const int64_t* part_row0, int a, int b, int64_
     const int64_t lo0 = part_row0[lo] / 256, lon = (part_row0[lo + 1] - part_row0[lo] + 255) / 256;
     const int64_t half = (lon + 1) / 2;
     return a < b ? (I - lo0) < half : (J - lo0) >= half;
+}
+
+void kmg_gram_i8_clear_cache() {
+    std::lock_guard<std::mutex> lk(g_tile_mu);
+    int cur = 0;
+    cudaGetDevice(&cur);
+    for (auto& kv : g_tile_cache) {
+        if (!kv.second.dev) continue;
+        if (kv.first.first != cur) cudaSetDevice(kv.first.first);
+        cudaFree(kv.second.dev);
+        if (kv.first.first != cur) cudaSetDevice(cur);
+    }
+    g_tile_cache.clear();
 }
 
 int kmg_gram_i8_launch(const GramI8Args* a, cudaStream_t stream) {
@@ -814,7 +948,11 @@ int kmg_gram_i8_launch(const GramI8Args* a, cudaStream_t stream) {
     static const int sync_waves = env_int("KMG_GEMM_SYNC", 1);
     static const int hint_mode = env_int("KMG_GEMM_HINT", 0);
     const bool sharded = a->n_parts > 0;
-    TileKey key{a->rows, a->cols, a->row_index0, a->col_index0, BM, (a->symmetric && !sharded) ? 1 : 0, band > 0 ? band : 8, 0, 0, {}, 0};
+    // The tile list of a plain block does not depend on where the block sits in the Gram; a symmetric block's depends on
+    // (row_index0 - col_index0) only; a sharded one's on (part, boundaries).  Keeping the origins out of the key lets the
+    // streamed block-rows, the row chunks of the host link and the ranks' offsets share one cached list.
+    const bool key_sym = a->symmetric && !sharded;
+    TileKey key{a->rows, a->cols, key_sym ? a->row_index0 - a->col_index0 : 0, 0, BM, key_sym ? 1 : 0, band > 0 ? band : 8, 0, 0, {}, 0, 0};
     if (a->mirror_all) {
         KMG_REQUIRE(!sharded && !a->symmetric && a->out_t != nullptr, KMG_ERR_ARG, "gram_i8: mirror_all is a plain block with a transposed copy");
         key.mirror_all = 1;
@@ -832,6 +970,8 @@ int kmg_gram_i8_launch(const GramI8Args* a, cudaStream_t stream) {
                     a->row_index0 == a->part_row0[a->part] && a->rows == a->part_row0[a->part + 1] - a->part_row0[a->part],
                     KMG_ERR_ARG, "gram_i8: block shape does not match the sharding");
         key.n_parts = a->n_parts; key.part = a->part;
+        static const int interleave = env_int("KMG_SHARD_INTERLEAVE", 1);
+        key.interleave = interleave;
     }
     TileList tl;
     rc = get_tiles(key, stream, &tl);
@@ -866,10 +1006,25 @@ int kmg_gram_i8_launch(const GramI8Args* a, cudaStream_t stream) {
         rc = get_counter(stream, &p.wave_counter);
         if (rc) return rc;
     }
-    p.hint_a = hint_mode == 1 ? ptx::L2_EVICT_LAST : ptx::L2_EVICT_NORMAL;
-    p.hint_b = hint_mode == 2 ? ptx::L2_EVICT_FIRST : ptx::L2_EVICT_NORMAL;
+    p.hint_a = (hint_mode & 1) ? ptx::L2_EVICT_LAST : ptx::L2_EVICT_NORMAL;   // bit 0: the band's A panels stay
+    p.hint_b = (hint_mode & 2) ? ptx::L2_EVICT_FIRST : ptx::L2_EVICT_NORMAL;  // bit 1: the B panels stream through
     // FP64-pipe instructions stall behind a saturated tensor pipe: integer conversion once the main loop dominates
-    if (pair) return a->Dpad >= 3072 ? launch_pair<true>(tmA, tmB, p, sms, stream) : launch_pair<false>(tmA, tmB, p, sms, stream);
+    if (pair) {
+        // Mirror stores through the TMA engine (cp.async.bulk.tensor) whenever the destination allows a tensor map: one
+        // destination (not the multi-destination single-launch sharded variant), 16-byte aligned base and row pitch.
+        static const int tma_mirror = env_int("KMG_GEMM_TMA_MIRROR", 1);
+        const int64_t esz = a->out_dtype == KMG_OUT_F64 ? 8 : 4;
+        const bool has_mirror = !sharded && (a->symmetric || a->mirror_all);
+        const bool use_tma = tma_mirror && has_mirror && (reinterpret_cast<uintptr_t>(p.mirror_base[0]) & 15) == 0 &&
+                             (p.ldo_t * esz) % 16 == 0 && p.ldo_t >= a->rows;
+        CUtensorMap tmT = tmA;  // placeholder when unused
+        if (use_tma) {
+            rc = make_mirror_map(&tmT, p.mirror_base[0], a->out_dtype, a->rows, a->cols, p.ldo_t);
+            if (rc) return rc;
+            return a->Dpad >= 3072 ? launch_pair<true, true>(tmA, tmB, tmT, p, sms, stream) : launch_pair<false, true>(tmA, tmB, tmT, p, sms, stream);
+        }
+        return a->Dpad >= 3072 ? launch_pair<true, false>(tmA, tmB, tmT, p, sms, stream) : launch_pair<false, false>(tmA, tmB, tmT, p, sms, stream);
+    }
     return m_sub == 1 ? launch<1>(tmA, tmB, p, sms, stream) : launch<2>(tmA, tmB, p, sms, stream);
 }
 

@@ -91,6 +91,21 @@ __device__ __forceinline__ void tma_load_2d_hint(void* smem_dst, const CUtensorM
         : "memory");
 }
 
+// 2-D tiled store shared -> global (bulk async-group completion).  c0 = inner coordinate.  The source must have been
+// written before a fence.proxy.async by every writing thread; elements outside the tensor map's extents are not written.
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* smem_src, int32_t c0, int32_t c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// all but the N most recent bulk groups of this thread have finished READING their shared-memory source
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+// ... have completed (writes performed)
+template <int N>
+__device__ __forceinline__ void tma_store_wait() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
+
 // grid-wide arrival counter helpers (wave barrier of the persistent GEMM)
 __device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
     uint32_t v;

@@ -100,12 +100,26 @@ def sharded_stage_bytes(part_row0, part, out_dtype=KMG_OUT_F64):
     return out.value
 
 
-def gram_i8_sharded(phi, part_row0, part, part_ptrs, ldo, out_dtype=KMG_OUT_F64, sd=None, stage=None):
+def sharded_launches(part_row0, part, exchange):
+    """GEMM launches one gram_i8_sharded call enqueues for this part."""
+    bounds = np.ascontiguousarray(part_row0, np.int64)
+    mode = {"single": _cabi.KMG_EXCH_SINGLE, "staged": _cabi.KMG_EXCH_STAGED, "direct": _cabi.KMG_EXCH_DIRECT}[exchange]
+    out = C.c_int(0)
+    check(_cabi.lib().kmg_gram_sharded_launches(bounds.size - 1, bounds.ctypes.data_as(C.c_void_p), int(part), mode, C.byref(out)))
+    return out.value
+
+
+def gram_i8_sharded(phi, part_row0, part, part_ptrs, ldo, out_dtype=KMG_OUT_F64, sd=None, stage=None, exchange=None):
     """Part `part`'s launch of the sharded symmetric Gram of all rows of `phi` (kmg_gram_i8_sharded_dev).
     part_row0: len(parts)+1 boundaries; part_ptrs: device address (int) of every part's block-row buffer (row stride ldo
-    elements) -- this device's own allocations or peer memory opened through CUDA IPC.  stage: device address of
-    sharded_stage_bytes() bytes of local staging (one launch + one peer copy per peer block) or None (single launch,
-    epilogue stores into the peers' buffers).  Returns the entries computed."""
+    elements) -- this device's own allocations or peer memory opened through CUDA IPC.  exchange: "direct" (one launch per
+    peer block, the epilogue's TMA stores write the owner's buffer), "staged" (stage = device address of
+    sharded_stage_bytes() bytes of local staging: one launch + one peer copy per peer block) or "single" (one launch,
+    thread-issued stores into the peers' buffers); default: "staged" when `stage` is given, else "single".
+    Returns the entries computed."""
+    if exchange is None:
+        exchange = "staged" if stage is not None else "single"
+    mode = {"single": _cabi.KMG_EXCH_SINGLE, "staged": _cabi.KMG_EXCH_STAGED, "direct": _cabi.KMG_EXCH_DIRECT}[exchange]
     n, W = phi.shape
     g = len(part_ptrs)
     bounds = np.ascontiguousarray(part_row0, np.int64)
@@ -113,7 +127,7 @@ def gram_i8_sharded(phi, part_row0, part, part_ptrs, ldo, out_dtype=KMG_OUT_F64,
     ptrs = (C.c_void_p * g)(*[int(p) for p in part_ptrs])
     computed = C.c_int64(0)
     check(_cabi.lib().kmg_gram_i8_sharded_dev(_p(phi), n, W, phi.stride(0), g, int(part), bounds.ctypes.data_as(C.c_void_p),
-                                              ptrs, int(ldo), out_dtype, _p(sd),
+                                              ptrs, int(ldo), out_dtype, _p(sd), mode,
                                               None if stage is None else C.c_void_p(int(stage)), C.byref(computed), _stream()))
     return computed.value
 
@@ -130,6 +144,25 @@ def mma_peak_i8(iters=20000, repeats=3):
         e1.record()
         torch.cuda.synchronize()
         best = max(best, ops.value / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+    return best
+
+
+ALU_PEAK_KINDS = {"lop3": 0, "shf": 1, "popc": 2, "dfma": 3, "dadd": 4, "dmul": 5}
+
+
+def alu_peak(kind, iters=4000, repeats=3):
+    """Measured issue peak of one CUDA-core instruction in thread-level instructions per second (kmg_alu_peak_dev timed
+    with CUDA events on the current stream): "lop3" / "shf" (INT32 ALU pipe), "popc" (XU), "dfma" / "dadd" / "dmul" (FP64)."""
+    _dev()
+    ops = C.c_int64(0)
+    best = 0.0
+    for _ in range(repeats + 1):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        check(_cabi.lib().kmg_alu_peak_dev(ALU_PEAK_KINDS[kind], int(iters), C.byref(ops), _stream()))
+        e1.record()
+        torch.cuda.synchronize()
+        best = max(best, ops.value / (e0.elapsed_time(e1) * 1e-3))
     return best
 
 

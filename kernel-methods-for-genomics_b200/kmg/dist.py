@@ -13,8 +13,10 @@ only where the path has a real exchange:
   * frobenius_sharded  ALIGNF's <K_i, K_j>_F style reductions: one all-reduce of a scalar per pair.
 
   * SymmetricShards  the mirror K[j,i] = K[i,j] (kernels.py:45) across GPUs: each rank computes only half of its
-                     block-row and the GEMM epilogue stores every tile twice, into its own buffer and -- transposed, over
-                     NVLink peer memory (CUDA IPC) -- into the owner's; no collective, one barrier at the end.
+                     block-row and the GEMM epilogue stores every tile twice, into its own buffer and -- transposed, by
+                     TMA bulk stores -- into staging that the copy engine ships to the owner over NVLink peer memory
+                     (CUDA IPC) piece by piece, or straight into the owner's buffer ("direct"); no collective, one
+                     barrier at the end.
 
 The partition / collective logic is backend agnostic (it is what the gloo tests cover); the arithmetic is supplied
 by the caller: `kmg.device` functions on the GPU, oracle functions in the CPU tests.
@@ -139,11 +141,19 @@ class SymmetricShards:
     """Block-row buffers of one n x n fp64 (or s32) Gram, one per rank of a single node, each visible to every other rank
     through CUDA IPC.  `build_spectrum` fills them with the sharded symmetric GEMM."""
 
-    def __init__(self, n, dtype=torch.float64, group=None, staged=True, ldo=None):
+    def __init__(self, n, dtype=torch.float64, group=None, exchange=None, ldo=None):
         """n: size of the symmetric square the ranks share; ldo >= n: row stride (and width) of every block-row buffer --
-        columns [n, ldo) are the caller's (e.g. the rest of a wider block-row, filled by a plain cross-Gram launch)."""
+        columns [n, ldo) are the caller's (e.g. the rest of a wider block-row, filled by a plain cross-Gram launch).
+        exchange: "staged" (default: transposed pieces into local staging, one copy-engine peer copy per piece while the
+        next launch runs), "direct" (the GEMM epilogue's TMA stores write the owner's buffer over NVLink: compute and
+        exchange in one kernel) or "single" (one launch, thread-issued peer stores); KMG_SYM_EXCHANGE overrides the
+        default.  Measured on 2 GPUs, n = 100 000 (profiles/r2_exchange_modes.txt): staged 32.8 ms, direct 39.7 ms, single
+        40.0 ms against 29.9 ms with no link at all -- SM-issued peer stores, by threads or by the TMA engine alike, slow
+        the GEMM itself although a store-only kernel reaches 717 GB/s on the same link (profiles/r2_p2p_store_probe.txt)."""
         import ctypes as C
-        self.staged = staged
+        import os
+        self.exchange = exchange or os.environ.get("KMG_SYM_EXCHANGE", "staged")
+        assert self.exchange in ("direct", "staged", "single")
         from . import _cabi
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -164,7 +174,7 @@ class SymmetricShards:
         payload, err = None, None
         try:
             _cabi.check(lib.kmg_dev_malloc((self.r1 - self.r0) * self.ldo * esz, C.byref(self._own)))
-            nbytes = kd.sharded_stage_bytes(self.bounds, self.rank, 1 if esz == 8 else 0)
+            nbytes = kd.sharded_stage_bytes(self.bounds, self.rank, 1 if esz == 8 else 0) if self.exchange == "staged" else 0
             if nbytes:  # local staging for the transposed blocks that the copy engine ships to their owners
                 _cabi.check(lib.kmg_dev_malloc(nbytes, C.byref(self._stage)))
             if self.world > 1:
@@ -197,6 +207,7 @@ class SymmetricShards:
             self._release()
             raise err
         self.ptrs[self.rank] = self._own.value
+        self.launches = kd.sharded_launches(self.bounds, self.rank, self.exchange)
         # this rank's block-row as a tensor (no copy): torch reads the CUDA array interface
         holder = type("_Buf", (), {})()
         holder.__cuda_array_interface__ = {"shape": (self.r1 - self.r0, self.ldo), "typestr": "<f8" if esz == 8 else "<i4",
@@ -210,7 +221,8 @@ class SymmetricShards:
         assert phi.shape[0] == self.n
         computed = kd.gram_i8_sharded(phi, self.bounds, self.rank, self.ptrs, self.ldo,
                                       out_dtype=1 if self.dtype == torch.float64 else 0, sd=sd,
-                                      stage=self._stage.value if (self._stage.value and self.staged) else None)
+                                      stage=self._stage.value if self.exchange == "staged" else None,
+                                      exchange=self.exchange if (self.exchange != "staged" or self._stage.value) else "single")
         return computed
 
     def finish(self):

@@ -75,8 +75,9 @@ def _nccl_worker(rank, world, port, q):
         full = kdist.gather_rows(blk, n)
         assert torch.equal(full, single)                            # NCCL all-gather materialises it everywhere
         # sharded SYMMETRIC build: half the MMA work per rank, mirror stores into the peers' buffers over CUDA IPC
-        for staged in (True, False):   # peer copies of staged blocks / epilogue stores straight into peer memory
-            shards = kdist.SymmetricShards(n, staged=staged)
+        # TMA stores into peer memory / peer copies of staged blocks / thread-issued stores into peer memory
+        for staged in ("direct", "staged", "single"):
+            shards = kdist.SymmetricShards(n, exchange=staged)
             for _ in range(2):
                 shards.block.fill_(-1.0)
                 torch.cuda.synchronize()

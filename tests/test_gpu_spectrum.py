@@ -225,20 +225,27 @@ def test_sharded_symmetric_gram_single_device(kd, world):
         torch.cuda.synchronize()
         assert torch.equal(torch.cat(bufs), ref), (world, ks, dt, "staged")
         assert computed2 == computed
+        # direct variant: one launch per peer block, mirror stores issued by the TMA engine into the owner's buffer
+        for b in bufs:
+            b.fill_(-7)
+        computed3 = [kd.gram_i8_sharded(phi, bounds, p, ptrs, n, out_dtype=dt, exchange="direct") for p in range(world)]
+        torch.cuda.synchronize()
+        assert torch.equal(torch.cat(bufs), ref), (world, ks, dt, "direct")
+        assert computed3 == computed
     # fused cosine normalisation through the mirror stores (kernels.py:398-415)
     phi = kd.spectrum_phi(planes, 101, [4])
     sd = kd.phi_diag_sqrt(phi)
     ref = kd.gram_i8(phi, phi, symmetric=True, sd_rows=sd, sd_cols=sd)
     bounds = kdist.sym_bounds(n, world)
     bufs = [torch.zeros((bounds[p + 1] - bounds[p], n), dtype=torch.float64, device="cuda") for p in range(world)]
-    for staged in (False, True):
+    for mode in ("single", "staged", "direct"):
         for b in bufs:
             b.zero_()
         for p in range(world):
-            st = torch.empty(max(kd.sharded_stage_bytes(bounds, p, 1), 8), dtype=torch.uint8, device="cuda") if staged else None
-            kd.gram_i8_sharded(phi, bounds, p, [b.data_ptr() for b in bufs], n, sd=sd, stage=st.data_ptr() if staged else None)
+            st = torch.empty(max(kd.sharded_stage_bytes(bounds, p, 1), 8), dtype=torch.uint8, device="cuda") if mode == "staged" else None
+            kd.gram_i8_sharded(phi, bounds, p, [b.data_ptr() for b in bufs], n, sd=sd, stage=None if st is None else st.data_ptr(), exchange=mode)
             torch.cuda.synchronize()
-        assert torch.equal(torch.cat(bufs), ref), staged
+        assert torch.equal(torch.cat(bufs), ref), mode
 
 
 def test_full_size_properties(kd):

@@ -18,7 +18,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--size", dest="n", type=int, default=100000)
 ap.add_argument("--iters", type=int, default=3)
 ap.add_argument("--dtype", default="f64")
-ap.add_argument("--staged", type=int, default=1)
+ap.add_argument("--exchange", default="direct")
 a = ap.parse_args()
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(local)
@@ -29,7 +29,7 @@ codes = onp.synthetic_codes(n, 101, seed=3)
 planes = kd.pack(codes, 0)
 phi = kd.spectrum_phi(planes, 101, list(range(1, 8)))
 dt = torch.float64 if a.dtype == "f64" else torch.int32
-shards = kdist.SymmetricShards(n, dtype=dt, staged=bool(a.staged))
+shards = kdist.SymmetricShards(n, dtype=dt, exchange=a.exchange)
 
 
 def timed(fn):
@@ -61,7 +61,7 @@ plain = [timed(lambda: kd.gram_i8(phi[shards.r0:shards.r1], phi, row_index0=shar
                                   out=shards.block)) for _ in range(a.iters + 1)]
 if rank == 0:
     best, bestp = min(ts[1:]), min(plain[1:])
-    print(f"world={world} n={n} {a.dtype} staged={a.staged}: sharded-symmetric {['%.2f' % t for t in ts]} ms -> {float(n) * n / best / 1e6:.1f} Gentries/s delivered | "
+    print(f"world={world} n={n} {a.dtype} exchange={a.exchange}: sharded-symmetric {['%.2f' % t for t in ts]} ms -> {float(n) * n / best / 1e6:.1f} Gentries/s delivered | "
           f"plain block-rows {['%.2f' % t for t in plain]} ms -> {float(n) * n / bestp / 1e6:.1f} Gentries/s | parity {'ok' if int(okt.item()) else 'MISMATCH'}",
           flush=True)
 shards.close()
