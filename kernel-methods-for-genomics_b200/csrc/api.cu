@@ -545,31 +545,23 @@ int kmg_gram_i8_dev(const int8_t* d_phi_rows, const int8_t* d_phi_cols, int64_t 
 //                     are one kernel, tile by tile, with no staging pass and no copy-engine pass through HBM.
 namespace {
 struct SubBlock { int b; int64_t r_lo, r_hi, c_lo, c_hi; };
-// The peer blocks part `a` computes, in launch order.  Full blocks (cyclic distance 1, 2, ... < g/2) come first, each cut
-// into KMG_SHARD_SPLIT (default 2) pieces by rows; the half block at distance g/2 goes last, right before the diagonal
-// block.  Why: every piece is followed by the copy (staged exchange) of its transposed image to the owner; a copy moves
-// 8 B/entry at ~0.78 TB/s, a launch produces 8 B/entry at ~0.67 TB/s, so the copy engine keeps pace piece by piece and
-// what is exposed at the end of the step is only the part of the LAST copy that the diagonal launch (no exchange) does
-// not cover.  With whole blocks and the half block first (round 1) the last copy was a full block: 6.4 ms of copy under
-// a 3.7 ms launch at 8 GPUs, n = 200 000.  Last = half a block cut in two: 1.6 ms.  At every phase rank a still sends to
-// (a + d) mod g -- a permutation, one incoming stream per receiver as long as the ranks stay in step.
+// The peer blocks part `a` computes, in launch order: the half block at distance g/2 first, then the full blocks at
+// cyclic distance 1, 2, ... < g/2, each cut into KMG_SHARD_SPLIT (default 2) pieces BY COLUMNS.  Every piece is followed
+// by the copy (staged exchange) of its transposed image to the owner while the next piece is computed, so what bounds the
+// step is  (first launch) + (all copies) -- the copy engine is the critical path (measured per-piece timeline, 8 GPUs,
+// n = 200 000, profiles/r2_shard_timeline.txt: a 5 GB block copies in 7.6 ms = 655 GB/s while its launch takes 7.4-8.0 ms,
+// and with whole blocks the last copy ended 3.5-4.6 ms after the last launch).  Hence:
+//   * pieces are cut by columns: the image of a piece is (columns of the piece) x (rows of the block), so its copy keeps
+//     the full 200 KB row width; cutting by rows halves the width and the 2-D copy drops to 430 GB/s (measured: 43.6 ms per
+//     step instead of 38.4);
+//   * the half block goes first: one of its two sides always has a narrow image (half the rows), its slow copy runs under
+//     the following launches instead of at the end;
+//   * the last copy is one piece of a full block (2.5 GB) under the diagonal launch (4 ms), which has no exchange.
+// At every phase rank a sends to (a + d) mod g -- a permutation, one incoming stream per receiver while the ranks stay in step.
 void sharded_plan(int g, const int64_t* bounds, int a, std::vector<SubBlock>* out) {
     static const int split_env = getenv("KMG_SHARD_SPLIT") ? atoi(getenv("KMG_SHARD_SPLIT")) : 2;
     const int split = split_env < 1 ? 1 : (split_env > 8 ? 8 : split_env);
     const int64_t a0 = bounds[a], a1 = bounds[a + 1];
-    auto push_split = [&](int b, int64_t r_lo, int64_t r_hi, int64_t c_lo, int64_t c_hi) {
-        const int64_t tiles = (r_hi - r_lo + 255) / 256;
-        int64_t lo = r_lo;
-        for (int q = 1; q <= split && lo < r_hi; ++q) {
-            const int64_t hi = q == split ? r_hi : std::min<int64_t>(r_hi, r_lo + (tiles * q / split) * 256);
-            if (hi > lo) out->push_back({b, lo, hi, c_lo, c_hi});
-            lo = hi;
-        }
-    };
-    for (int d = 1; d < g; ++d) {
-        const int b = (a + d) % g;
-        if (2 * d < g) push_split(b, a0, a1, bounds[b], bounds[b + 1]);
-    }
     if (g % 2 == 0 && g > 1) {
         // distance g/2: split by the lower-numbered part's row tiles, as kmg_gram_sharded_takes does
         const int b = (a + g / 2) % g;
@@ -577,8 +569,20 @@ void sharded_plan(int g, const int64_t* bounds, int a, std::vector<SubBlock>* ou
         const int lo = a < b ? a : b;
         const int64_t lon = (bounds[lo + 1] - bounds[lo] + 255) / 256;
         const int64_t cut = std::min<int64_t>(bounds[lo] + (lon + 1) / 2 * 256, bounds[lo + 1]);
-        if (a < b) { if (cut > a0) push_split(b, a0, cut, b0, b1); }
-        else if (cut < b1) push_split(b, a0, a1, cut, b1);
+        if (a < b) { if (cut > a0) out->push_back({b, a0, cut, b0, b1}); }
+        else if (cut < b1) out->push_back({b, a0, a1, cut, b1});
+    }
+    for (int d = 1; d < g; ++d) {
+        if (2 * d >= g) break;
+        const int b = (a + d) % g;
+        const int64_t b0 = bounds[b], b1 = bounds[b + 1];
+        const int64_t tiles = (b1 - b0 + 255) / 256;
+        int64_t lo = b0;
+        for (int q = 1; q <= split && lo < b1; ++q) {
+            const int64_t hi = q == split ? b1 : std::min<int64_t>(b1, b0 + (tiles * q / split) * 256);
+            if (hi > lo) out->push_back({b, a0, a1, lo, hi});
+            lo = hi;
+        }
     }
 }
 size_t stage_align(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -637,6 +641,17 @@ int kmg_gram_i8_sharded_dev(const int8_t* d_phi, int64_t n, int64_t width, int64
     int rc;
     cudaStream_t s0, copy;
     if ((rc = kmg_rt_get_streams(&s0, &copy))) return rc;
+    // KMG_SHARD_COPY_STREAMS=2: consecutive pieces alternate between two copy streams (two copy engines at work)
+    static const int n_copy = getenv("KMG_SHARD_COPY_STREAMS") ? atoi(getenv("KMG_SHARD_COPY_STREAMS")) : 1;
+    static cudaStream_t copy2[64] = {};
+    cudaStream_t copies[2] = {copy, copy};
+    if (n_copy >= 2) {
+        int dev = 0;
+        KMG_CUDA_CHECK(cudaGetDevice(&dev));
+        if (copy2[dev & 63] == nullptr) KMG_CUDA_CHECK(cudaStreamCreateWithFlags(&copy2[dev & 63], cudaStreamNonBlocking));
+        copies[1] = copy2[dev & 63];
+    }
+    int piece = 0;
     std::vector<SubBlock> plan;
     sharded_plan(n_parts, part_row0, part, &plan);
     // (Round 1, 8 GPUs, n = 200 000, whole blocks with the half block first: 38.5 ms/step, 35.3 ms of it the GEMM phase
@@ -646,6 +661,16 @@ int kmg_gram_i8_sharded_dev(const int8_t* d_phi, int64_t n, int64_t width, int64
     char* stage = static_cast<char*>(d_stage);
     int64_t total = 0, got = 0;
     cudaEvent_t ev;
+    // KMG_SHARD_TRACE=1 (debug): time every launch and every copy of this call with events and print the timeline
+    static const bool trace = getenv("KMG_SHARD_TRACE") != nullptr;
+    std::vector<cudaEvent_t> tg, tc;
+    auto mark = [&](std::vector<cudaEvent_t>& v, cudaStream_t st) {
+        if (!trace) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, st);
+        v.push_back(e);
+    };
     for (const SubBlock& sb : plan) {
         const int64_t rows = sb.r_hi - sb.r_lo, cols = sb.c_hi - sb.c_lo;
         memset(&a, 0, sizeof(a));
@@ -657,16 +682,21 @@ int kmg_gram_i8_sharded_dev(const int8_t* d_phi, int64_t n, int64_t width, int64
         char* dst = static_cast<char*>(part_out[sb.b]) + ((sb.c_lo - part_row0[sb.b]) * ldo + sb.r_lo) * esz;
         if (staged) { a.out_t = stage; a.ldo_t = rows; }
         else { a.out_t = dst; a.ldo_t = ldo; }   // direct: the epilogue's TMA stores go to the owner's memory
+        mark(tg, s);
         if ((rc = kmg_gram_i8_launch(&a, s))) return rc;
+        mark(tg, s);
         total += got;
         if (!staged) continue;
         // the transposed block (cols x rows, contiguous) -> rows [c_lo, c_hi) x columns [r_lo, r_hi) of the owner's block-row
+        cudaStream_t cs = copies[piece++ & 1];
         KMG_CUDA_CHECK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
         KMG_CUDA_CHECK(cudaEventRecord(ev, s));
-        KMG_CUDA_CHECK(cudaStreamWaitEvent(copy, ev, 0));
+        KMG_CUDA_CHECK(cudaStreamWaitEvent(cs, ev, 0));
         KMG_CUDA_CHECK(cudaEventDestroy(ev));
+        mark(tc, cs);
         KMG_CUDA_CHECK(cudaMemcpy2DAsync(dst, (size_t)(ldo * esz), stage, (size_t)(rows * esz), (size_t)(rows * esz), (size_t)cols,
-                                         cudaMemcpyDefault, copy));
+                                         cudaMemcpyDefault, cs));
+        mark(tc, cs);
         stage += stage_align((size_t)(rows * cols * esz));
     }
     // diagonal block: the single-GPU symmetric build on this part's own square
@@ -675,13 +705,40 @@ int kmg_gram_i8_sharded_dev(const int8_t* d_phi, int64_t n, int64_t width, int64
     a.row_index0 = a0; a.col_index0 = a0; a.out = my + a0 * esz; a.ldo = ldo; a.out_dtype = out_dtype;
     a.symmetric = 1; a.out_t = a.out; a.ldo_t = ldo;
     a.sd_rows = d_sd ? d_sd + a0 : nullptr; a.sd_cols = a.sd_rows; a.computed_entries = &got;
+    mark(tg, s);
     if ((rc = kmg_gram_i8_launch(&a, s))) return rc;
+    mark(tg, s);
     total += got;
+    if (trace) {
+        cudaStreamSynchronize(s);
+        cudaStreamSynchronize(copies[0]);
+        cudaStreamSynchronize(copies[1]);
+        char line[2048];
+        int o = snprintf(line, sizeof(line), "[shard trace part %d] gemm:", part);
+        for (size_t i = 0; i + 1 < tg.size(); i += 2) {
+            float t0 = 0, t1 = 0;
+            cudaEventElapsedTime(&t0, tg[0], tg[i]);
+            cudaEventElapsedTime(&t1, tg[0], tg[i + 1]);
+            o += snprintf(line + o, sizeof(line) - o, " [%.2f-%.2f]", t0, t1);
+        }
+        o += snprintf(line + o, sizeof(line) - o, " copy:");
+        for (size_t i = 0; i + 1 < tc.size(); i += 2) {
+            float t0 = 0, t1 = 0;
+            cudaEventElapsedTime(&t0, tg[0], tc[i]);
+            cudaEventElapsedTime(&t1, tg[0], tc[i + 1]);
+            o += snprintf(line + o, sizeof(line) - o, " [%.2f-%.2f]", t0, t1);
+        }
+        fprintf(stderr, "%s\n", line);
+        for (cudaEvent_t e : tg) cudaEventDestroy(e);
+        for (cudaEvent_t e : tc) cudaEventDestroy(e);
+    }
     if (staged) {  // `stream` completes only after the peer copies have
-        KMG_CUDA_CHECK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-        KMG_CUDA_CHECK(cudaEventRecord(ev, copy));
-        KMG_CUDA_CHECK(cudaStreamWaitEvent(s, ev, 0));
-        KMG_CUDA_CHECK(cudaEventDestroy(ev));
+        for (int q = 0; q < (copies[1] != copies[0] ? 2 : 1); ++q) {
+            KMG_CUDA_CHECK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+            KMG_CUDA_CHECK(cudaEventRecord(ev, copies[q]));
+            KMG_CUDA_CHECK(cudaStreamWaitEvent(s, ev, 0));
+            KMG_CUDA_CHECK(cudaEventDestroy(ev));
+        }
     }
     if (computed_entries) *computed_entries = total;
     return KMG_OK;
