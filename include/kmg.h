@@ -111,6 +111,35 @@ int kmg_alignf_stats_host(const double* const* Ks, int p, int64_t n, const int64
 int kmg_nlck_grad_host(const double* const* Ks_fit, int p, int64_t nfit, const double* u, const double* alpha, int degree,
                        double* grad);
 
+/* ---- fused ALIGNF / NLCK entry points: sequences in, statistics / combination out ------------ */
+/* One kernel of a method list -- what select_method's mini-language names (kernels.py:461-505). */
+#define KMG_KIND_SP 0   /* SP_k{k}                    get_spectrum_K, unnormalised */
+#define KMG_KIND_MM 1   /* MM_k{k}_m{m}               get_mismatch_K, normalised as the reference returns it */
+#define KMG_KIND_WD 2   /* WD_d{d} */
+#define KMG_KIND_WDS 3  /* WDS_d{d}_s{S} */
+#define KMG_KIND_LA 4   /* LA_e{e}_d{dd}_b{beta}_smith{smith}: the intended recursion (see kmg_la_host) */
+typedef struct kmg_method {
+    int32_t kind, k, m, d, S, smith;
+    double e, dd, beta;
+} kmg_method_t;
+/* ALIGNF.__init__ Gram side (ALIGNF.py:28-29,36-58) from SEQUENCES: for every method the fit sub-block K[idx][:, idx] is
+ * built on the device straight from the gathered sequences -- the producing kernel's epilogue emits the centring
+ * statistics (row sums) and K y~ -- and a_i = <Kc_i, y y'>_F, M_ij = <Kc_i, Kc_j>_F come back: p + p^2 doubles, no Gram
+ * crosses PCIe.  pcie_bytes (nullable, 2 entries): bytes moved host->device / device->host by this call. */
+int kmg_alignf_fused_host(const uint8_t* seqs, int64_t n, int L, int seq_format, const kmg_method_t* methods, int p,
+                          const int64_t* idx, int64_t nfit, const double* y, double* a, double* M, int64_t* pcie_bytes);
+/* ALIGNF.get_K (ALIGNF.py:93; degree 1, normalize_inputs 0, normalize 0) and NLCK.get_K (NLCKernels.py:97-99; every kernel
+ * through normalize_K first, then (sum_m u_m K_m)**degree and normalize_K of the result) from SEQUENCES: one Gram launch per
+ * method accumulates u_m K_m into the output in its epilogue -- bit-identical to the reference's sum over stacked kernels --
+ * and the last one applies the power and the final normalisation; only Km (n x n, row stride ldk) crosses PCIe. */
+int kmg_combine_fused_host(const uint8_t* seqs, int64_t n, int L, int seq_format, const kmg_method_t* methods, int p,
+                           const double* u, int degree, int normalize_inputs, int normalize, double* Km, int64_t ldk, int64_t* pcie_bytes);
+/* The Grams of a method list over the sequences idx[0..nsel) (idx NULL: all n) as DEVICE-resident nsel x nsel fp64 matrices
+ * in the caller's buffers d_out[0..p) (kmg_dev_malloc): NLCK's fit sub-blocks (NLCKernels.py:33,36) without an upload;
+ * normalize_inputs = 1 applies normalize_K to every kernel as NLCK.normalize_kernels does (NLCKernels.py:43-48). */
+int kmg_build_grams_dev(const uint8_t* seqs, int64_t n, int L, int seq_format, const kmg_method_t* methods, int p,
+                        const int64_t* idx, int64_t nsel, int normalize_inputs, void* const* d_out);
+
 /* ---- device-pointer entry points (block-row construction) ---------------------------------- */
 /* letter_to_num/format (kernels.py:178-193): n x L bytes -> 8 u32 words of bit-planes per sequence.
  * *d_err_flag (device int, zero-initialised by the caller) is set to 1 on a non-ACGT byte. */

@@ -45,6 +45,28 @@ class ALIGNF():
         self.a, self.M = a.T, M
         self.u_star = self.get_v()
 
+    @classmethod
+    def from_sequences(cls, seqs, methods, idx, y):
+        """The same object from SEQUENCES: `seqs` are all n sequences in kernel order, `methods` the reference's method
+        strings, `idx` the fit rows, `y` their labels.  a and M come from one fused call (kmg.fused.alignf_stats: the fit
+        sub-blocks are built, centred and reduced on the device; p + p^2 doubles come back), get_K from another
+        (kmg.fused.combine: every Gram launch adds u_i K_i to the result in its epilogue).  No n x n kernel is built on
+        the host at any point."""
+        from kmg import fused as _fused
+        self = cls.__new__(cls)
+        self.X = self.ID = self.kernels = None
+        self._seqs, self._methods = seqs, list(methods)
+        self.idx = np.atleast_1d(np.asarray(idx))
+        self.y = np.asarray(y, dtype=np.float64)
+        self.p = len(self._methods)
+        self.Nfeval = 1
+        for stage in ('Centering kernels...', 'Computing vector a...', 'Computing matrix M...'):
+            print(stage)
+        a, M = _fused.alignf_stats(seqs, self._methods, self.idx, self.y)
+        self.a, self.M = a.T, M
+        self.u_star = self.get_v()
+        return self
+
     # ---- pieces of the reference's interface that callers may still reach for
     @property
     def Y(self):
@@ -93,6 +115,9 @@ class ALIGNF():
     def get_K(self):
         """Km = sum_i u*_i K_i over the full, uncentred kernels (ALIGNF.py:91-94)."""
         print('Alignment vector : ', self.u_star, '\n' + '-' * 61)
+        if self.kernels is None:  # built from sequences: accumulate u_i K_i in the Gram epilogues
+            from kmg import fused as _fused
+            return _fused.combine(self._seqs, self._methods, self.u_star, degree=1)
         return _host.combine(self.kernels, self.u_star, degree=1)
 
 

@@ -1,8 +1,9 @@
 """
 NLCKernels.py -- drop-in for the reference's NLCKernels.py with the Gram-side algebra on the GPU.
 
-Public surface as in the reference (NLCKernels.py:12-100): class `NLCK(X, y, ID, kernels, C, eps, degree)` with
-`normalize_kernels`, `svm_step`, `grad`, `normalize`, `fit`, `get_K`.
+Public surface as in the reference (NLCKernels.py:12-150): class `NLCK(X, y, ID, kernels, C, eps, degree)` with
+`normalize_kernels`, `svm_step`, `grad`, `normalize`, `fit`, `get_K`, and the module-level `cross_validation` harness
+(host glue, NLCKernels.py:103-150).
 
 What runs in libkmg.so:
   * normalize_kernels: normalize_K of every kernel, in place (NLCKernels.py:43-48),
@@ -41,6 +42,26 @@ class NLCK():
         self.C, self.eps, self.degree = C, eps, degree
         self.lbda = 1 / (2 * self.C * self.n)
         self._fit_dev = None  # fit sub-blocks resident in HBM for the whole projected-gradient loop
+
+    @classmethod
+    def from_sequences(cls, seqs, methods, idx, y, C=1e-5, eps=1e-8, degree=2):
+        """The same object from SEQUENCES: `seqs` are all n sequences in kernel order, `methods` the reference's method
+        strings, `idx` the fit rows, `y` their labels.  The normalised fit sub-blocks (NLCKernels.py:33,36) are built on the
+        device and stay there for every iteration (kmg.fused.resident_grams), and get_K accumulates u_m K_m, the power and
+        the final normalisation in the Gram epilogues (kmg.fused.combine): no n x n kernel is built on the host."""
+        from kmg import fused as _fused
+        self = cls.__new__(cls)
+        self.X = self.ID = self.kernels = self.kernels_fit = None
+        self._seqs, self._methods = seqs, list(methods)
+        self.idx = np.atleast_1d(np.asarray(idx))
+        self.y = np.asarray(y, dtype=np.float64)
+        self.n = self.y.shape[0]
+        self.p = len(self._methods)
+        self.C, self.eps, self.degree = C, eps, degree
+        self.lbda = 1 / (2 * self.C * self.n)
+        grams = _fused.resident_grams(seqs, self._methods, self.idx, normalize_inputs=True)
+        self._fit_dev = (grams, _res.QuadForms(grams), _res.DeviceGram(self.n))
+        return self
 
     def _resident(self):
         """Upload the p fit sub-blocks once; svm_step and grad then re-use them every iteration."""
@@ -106,5 +127,40 @@ class NLCK():
         u_star = self.fit(u0, fnorm, n_iter, eta)
         print('Alignment vector : ', u_star)
         print('Normalizing final kernel...')
+        if self.kernels is None:  # built from sequences: accumulate, power and normalisation in the Gram epilogues
+            from kmg import fused as _fused
+            return _fused.combine(self._seqs, self._methods, u_star, degree=self.degree, normalize_inputs=True, normalize=True)
         # combination, power and normalize_K (including its K[0,0]==1 early-out) in one device pass
         return _host.combine(self.kernels, u_star, degree=self.degree, normalize=True)
+
+
+def cross_validation(k, methods, Cs_NLK, Cs_SVM, degrees, lambdas):
+    """Grid search over NLCK's (C, degree, lambda) with an inner 3-fold search of the C-SVM constant -- the harness of
+    NLCKernels.py:103-150, called by main.py:72.  Host-side glue only: every Gram it touches comes from
+    `utils.get_all_data` (this repo's `kernels.select_method` behind it) and every combination from `NLCK.get_K` above.
+    `utils`, pandas and itertools belong to the caller's environment (the reference's utils.py needs cvxopt), so they are
+    imported here, not at module load.
+
+    k: data set 1..3; methods: kernel method strings; Cs_NLK / degrees / lambdas: the NLCK grid (`lambda` is get_K's
+    `fnorm`); Cs_SVM: candidates for the C-SVM constant.  Returns a DataFrame with one row per grid point and the columns
+    'methods', 'C NLCK', 'd', 'lambda', 'Best C CSVM', 'val acc'."""
+    from itertools import product
+
+    import pandas as pd
+    import utils
+
+    data, data1, data2, data3, kernels, ID = utils.get_all_data(methods)
+    p = len(kernels)
+    grid = list(product(Cs_NLK, degrees, lambdas))
+    blank = np.zeros(len(grid))
+    results = pd.DataFrame({'methods': [methods] * len(grid), 'C NLCK': blank, 'd': blank, 'lambda': blank,
+                            'Best C CSVM': blank, 'val acc': blank})
+    X_train, y_train, X_val, y_val, X_test, kernels, ID = utils.reformat_data((data1, data2, data3)[k - 1], kernels, ID)
+    for row, (C, d, lbda) in enumerate(grid):
+        print('NLCK C={}, degree={}, lambda={}'.format(C, d, lbda))
+        Km = NLCK(X_train, y_train, ID, kernels, C=C, eps=1e-9, degree=d).get_K(fnorm=lbda)
+        C_opt, _, _, _, mean_scores_te = utils.cross_validation(
+            Ps=Cs_SVM, data=[X_train, y_train, X_val, y_val, X_test], algo='CSVM', kfolds=3, K=Km, ID=ID,
+            pickleName='cv_C_SVM_NLCK_C{}_d{}_l{}_p{}_k{}.pkl'.format(C, d, lbda, p, k))
+        results.iloc[row, 1:6] = C, d, lbda, C_opt, np.max(mean_scores_te)
+    return results

@@ -19,6 +19,7 @@
 #include <vector>
 
 #include "../../include/kmg.h"
+#include "api_internal.h"
 #include "elementwise.h"
 #include "gram_i8.h"
 #include "kmg_common.cuh"
@@ -113,6 +114,11 @@ int pair_block(void* c, int64_t r0, int64_t rows, void* out, int64_t ldo, int sy
 }
 
 }  // namespace
+
+int kmg_api_upload_planes(const uint8_t* seqs, int64_t n, int L, int fmt, DevBuf* planes, cudaStream_t s) {
+    KMG_REQUIRE(n >= 0 && (seqs != nullptr || n == 0), KMG_ERR_ARG, "bad sequence buffer");
+    return upload_planes(seqs, n, L, fmt, planes, s);
+}
 
 // ------------------------------------------------------------------------------------------
 // library
@@ -432,25 +438,30 @@ int kmg_alignf_stats_host(const double* const* Ks, int p, int64_t n, const int64
     if (nfit == 0) { for (int i = 0; i < p; ++i) { a[i] = 0; for (int j = 0; j < p; ++j) M[i * p + j] = 0; } return KMG_OK; }
     cudaStream_t s;
     if ((rc = kmg_rt_get_streams(&s, nullptr))) return rc;
-    DevBuf full, sub, didx, dy, ws, part, res;
+    DevBuf sub, dy, ws, part, res;
     std::vector<DevBuf> kc(p);
-    if ((rc = full.alloc((size_t)n * n * 8))) return rc;
     if ((rc = sub.alloc((size_t)nfit * nfit * 8))) return rc;
-    if ((rc = didx.alloc((size_t)nfit * 8))) return rc;
     if ((rc = dy.alloc((size_t)nfit * 8))) return rc;
     if ((rc = ws.alloc((size_t)kmg_ew_center_workspace(nfit)))) return rc;
     if ((rc = part.alloc((size_t)nfit * 8))) return rc;
     if ((rc = res.alloc((size_t)(p + p * p) * 8))) return rc;
-    KMG_CUDA_CHECK(cudaMemcpyAsync(didx.p, idx, (size_t)nfit * 8, cudaMemcpyHostToDevice, s));
     KMG_CUDA_CHECK(cudaMemcpyAsync(dy.p, y, (size_t)nfit * 8, cudaMemcpyHostToDevice, s));
+    // The sub-block K[idx][:, idx] (ALIGNF.py:28) is gathered on the host: nfit^2 doubles cross PCIe per kernel instead
+    // of the full n^2 matrix (run.py's sizes: 18 MB instead of 72 MB per kernel and data set).
+    std::vector<double> hsub((size_t)nfit * nfit);
     for (int i = 0; i < p; ++i) {
         if ((rc = kc[i].alloc((size_t)nfit * nfit * 8))) return rc;
-        KMG_CUDA_CHECK(cudaMemcpyAsync(full.p, Ks[i], (size_t)n * n * 8, cudaMemcpyHostToDevice, s));
-        if ((rc = kmg_ew_gather(full.as<double>(), n, didx.as<int64_t>(), nfit, sub.as<double>(), nfit, s))) return rc;   // ALIGNF.py:28
+        const double* K = Ks[i];
+        for (int64_t a = 0; a < nfit; ++a) {
+            const double* row = K + idx[a] * n;
+            double* dst = hsub.data() + a * nfit;
+            for (int64_t b = 0; b < nfit; ++b) dst[b] = row[idx[b]];
+        }
+        KMG_CUDA_CHECK(cudaMemcpyAsync(sub.p, hsub.data(), (size_t)nfit * nfit * 8, cudaMemcpyHostToDevice, s));
         if ((rc = kmg_ew_center(sub.as<double>(), nfit, nfit, kc[i].as<double>(), nfit, ws.p, s))) return rc;              // ALIGNF.py:36-41
         // a_i = sum(Kc_i * y y')  (ALIGNF.py:43-48)
         if ((rc = kmg_ew_weighted_dot(kc[i].as<double>(), nfit, nullptr, 0, dy.as<double>(), nfit, part.as<double>(), res.as<double>() + i, s))) return rc;
-        KMG_CUDA_CHECK(cudaStreamSynchronize(s));  // `full` is reused by the next kernel's upload
+        KMG_CUDA_CHECK(cudaStreamSynchronize(s));  // `hsub` / `sub` are reused by the next kernel
     }
     for (int i = 0; i < p; ++i)
         for (int j = i; j < p; ++j)  // M_ij = sum(Kc_i * Kc_j)  (ALIGNF.py:50-58)

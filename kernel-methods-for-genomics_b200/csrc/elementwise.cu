@@ -15,6 +15,7 @@
 #include <stdint.h>
 
 #include "elementwise.h"
+#include "epi_ops.cuh"
 #include "kmg_common.cuh"
 
 namespace {
@@ -189,21 +190,87 @@ __global__ void __launch_bounds__(256) combine_kernel(CombineParams cp, int64_t 
 }
 
 // partial[b] = sum over the block's elements of A_ij * (B ? B_ij : 1) * (w ? w_i w_j : 1)
+// With rA / rB (row sums of the symmetric A / B) and gA / gB (their grand sums) the factors are centred on the fly,
+// Ac_ij = A_ij - rA_j/n - rA_i/n + gA/n^2 -- the entries of (I-11'/n) A (I-11'/n) (kernels.py:387-395) without storing them.
 __global__ void __launch_bounds__(256) weighted_dot_partial_kernel(const double* __restrict__ A, int64_t lda, const double* __restrict__ B,
                                                                    int64_t ldb, const double* __restrict__ w, int64_t n,
-                                                                   double* __restrict__ partial) {
+                                                                   double* __restrict__ partial, const double* __restrict__ rA,
+                                                                   const double* __restrict__ gA, const double* __restrict__ rB,
+                                                                   const double* __restrict__ gB) {
     __shared__ double sh[8];
     const int64_t i = blockIdx.x;
     double acc = 0.0;
     const double wi = w ? w[i] : 1.0;
+    const double inv = 1.0 / (double)n;
+    const double ai = rA ? rA[i] * inv : 0.0, ag = rA ? (*gA) * inv * inv : 0.0;
+    const double bi = rB ? rB[i] * inv : 0.0, bg = rB ? (*gB) * inv * inv : 0.0;
     for (int64_t j = threadIdx.x; j < n; j += 256) {
         double v = A[i * lda + j];
-        if (B) v *= B[i * ldb + j];
+        if (rA) v = v - rA[j] * inv - ai + ag;   // same association as center_apply_kernel
+        if (B) {
+            double b = B[i * ldb + j];
+            if (rB) b = b - rB[j] * inv - bi + bg;
+            v *= b;
+        }
         if (w) v *= w[j];
         acc += v;
     }
     acc = block_sum(acc, sh);
     if (threadIdx.x == 0) partial[i] = acc * wi;
+}
+
+// out[r] = sum over chunks (in order) of partial[r][chunk]: the second, fixed-order stage of the epilogue row statistics
+__global__ void __launch_bounds__(256) partial_rows_reduce_kernel(const double* __restrict__ partial, int64_t rows, int64_t n_chunks,
+                                                                  double* __restrict__ out) {
+    const int64_t r = blockIdx.x * 256ll + threadIdx.x;
+    if (r >= rows) return;
+    double acc = 0.0;
+    for (int64_t c = 0; c < n_chunks; ++c) acc += partial[r * n_chunks + c];
+    out[r] = acc;
+}
+
+__global__ void __launch_bounds__(256) vec_dot_kernel(const double* __restrict__ a, const double* __restrict__ b, int64_t n, double* __restrict__ out) {
+    __shared__ double sh[8];
+    double acc = 0.0;
+    for (int64_t i = threadIdx.x; i < n; i += 256) acc += a[i] * b[i];
+    acc = block_sum(acc, sh);
+    if (threadIdx.x == 0) *out = acc;
+}
+
+// rows of K times a weight vector: out[r] = sum_j K[r][j] w[j] (one warp per row)
+__global__ void __launch_bounds__(256) row_wsum_kernel(const double* __restrict__ K, int64_t rows, int64_t cols, int64_t ld,
+                                                       const double* __restrict__ w, double* __restrict__ out) {
+    const int64_t row = blockIdx.x * 8ll + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    double acc = 0.0;
+    for (int64_t j = lane; j < cols; j += 32) acc += K[row * ld + j] * w[j];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) out[row] = acc;
+}
+
+__global__ void __launch_bounds__(256) gather_vec_kernel(const double* __restrict__ v, const int64_t* __restrict__ idx, int64_t m, double* __restrict__ out) {
+    const int64_t t = blockIdx.x * 256ll + threadIdx.x;
+    if (t < m) out[t] = v[idx[t]];
+}
+
+// accumulate a stored Gram into a combination the way the fused epilogues do (for kernels whose producer has no
+// fused normalisation, epi_ops.cuh): out = [out +] u * (K / (sd_i sd_j), diag 1), then power / normalisation of the last term
+__global__ void __launch_bounds__(256) accumulate_kernel(const double* __restrict__ K, int64_t ldk, const double* __restrict__ sd, EpiOps e,
+                                                         int64_t n, double* __restrict__ out, int64_t ldo) {
+    const int64_t j = blockIdx.x * 256ll + threadIdx.x;
+    if (j >= n) return;
+    for (int64_t i = blockIdx.y; i < n; i += gridDim.y) {
+        double v = K[i * ldk + j];
+        if (sd != nullptr) {
+            v = __ddiv_rn(v, __dmul_rn(sd[i], sd[j]));
+            if (i == j) v = 1.0;
+        }
+        const double prev = e.accumulate == 2 ? out[i * ldo + j] : 0.0;
+        const bool nrm = e.post_sd_rows != nullptr;
+        out[i * ldo + j] = epi_finish(e, v, prev, i == j, nrm ? e.post_sd_rows[i] : 1.0, nrm ? e.post_sd_cols[j] : 1.0);
+    }
 }
 
 // s32 counts -> u16 for the host link (host_link.cu d2h_rows widens them back to double): 8 entries per thread, 16-byte
@@ -298,8 +365,57 @@ int kmg_ew_combine(const double* const* Ks, const int64_t* lds, const double* u,
 int kmg_ew_weighted_dot(const double* A, int64_t lda, const double* B, int64_t ldb, const double* w, int64_t n, double* partial,
                         double* result, cudaStream_t s) {
     if (n <= 0) return KMG_OK;
-    weighted_dot_partial_kernel<<<(unsigned)n, 256, 0, s>>>(A, lda, B, ldb, w, n, partial);
+    weighted_dot_partial_kernel<<<(unsigned)n, 256, 0, s>>>(A, lda, B, ldb, w, n, partial, nullptr, nullptr, nullptr, nullptr);
     vec_sum_kernel<<<1, 256, 0, s>>>(partial, n, result);
+    KMG_CUDA_CHECK(cudaGetLastError());
+    return KMG_OK;
+}
+
+int kmg_ew_centered_dot(const double* A, int64_t lda, const double* rA, const double* gA, const double* B, int64_t ldb, const double* rB,
+                        const double* gB, int64_t n, double* partial, double* result, cudaStream_t s) {
+    if (n <= 0) return KMG_OK;
+    weighted_dot_partial_kernel<<<(unsigned)n, 256, 0, s>>>(A, lda, B, ldb, nullptr, n, partial, rA, gA, rB, gB);
+    vec_sum_kernel<<<1, 256, 0, s>>>(partial, n, result);
+    KMG_CUDA_CHECK(cudaGetLastError());
+    return KMG_OK;
+}
+
+int kmg_ew_partial_rows_reduce(const double* partial, int64_t rows, int64_t n_chunks, double* out, cudaStream_t s) {
+    if (rows <= 0) return KMG_OK;
+    partial_rows_reduce_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, s>>>(partial, rows, n_chunks, out);
+    KMG_CUDA_CHECK(cudaGetLastError());
+    return KMG_OK;
+}
+
+int kmg_ew_vec_sum(const double* v, int64_t n, double* out, cudaStream_t s) {
+    vec_sum_kernel<<<1, 256, 0, s>>>(v, n, out);
+    KMG_CUDA_CHECK(cudaGetLastError());
+    return KMG_OK;
+}
+
+int kmg_ew_vec_dot(const double* a, const double* b, int64_t n, double* out, cudaStream_t s) {
+    vec_dot_kernel<<<1, 256, 0, s>>>(a, b, n, out);
+    KMG_CUDA_CHECK(cudaGetLastError());
+    return KMG_OK;
+}
+
+int kmg_ew_row_wsums(const double* K, int64_t rows, int64_t cols, int64_t ld, const double* w, double* out, cudaStream_t s) {
+    if (rows <= 0) return KMG_OK;
+    row_wsum_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, s>>>(K, rows, cols, ld, w, out);
+    KMG_CUDA_CHECK(cudaGetLastError());
+    return KMG_OK;
+}
+
+int kmg_ew_gather_vec(const double* v, const int64_t* idx, int64_t m, double* out, cudaStream_t s) {
+    if (m <= 0) return KMG_OK;
+    gather_vec_kernel<<<(unsigned)((m + 255) / 256), 256, 0, s>>>(v, idx, m, out);
+    KMG_CUDA_CHECK(cudaGetLastError());
+    return KMG_OK;
+}
+
+int kmg_ew_accumulate(const double* K, int64_t ldk, const double* sd, const EpiOps* e, int64_t n, double* out, int64_t ldo, cudaStream_t s) {
+    if (n <= 0) return KMG_OK;
+    accumulate_kernel<<<dim3((unsigned)((n + 255) / 256), (unsigned)std::min<int64_t>(n, 65535)), 256, 0, s>>>(K, ldk, sd, *e, n, out, ldo);
     KMG_CUDA_CHECK(cudaGetLastError());
     return KMG_OK;
 }

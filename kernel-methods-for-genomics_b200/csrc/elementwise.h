@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "epi_ops.cuh"
+
 #define KMG_MAX_COMBINE 16
 
 int kmg_ew_diag_sqrt(const double* K, int64_t n, int64_t ld, double* sd, cudaStream_t s);
@@ -22,3 +24,15 @@ int64_t kmg_ew_col_sums_workspace(int64_t rows, int64_t cols);
 int kmg_ew_col_sums(const double* K, int64_t rows, int64_t cols, int64_t ld, double* cs, void* workspace, cudaStream_t s);
 int kmg_ew_center_apply(const double* K, int64_t rows, int64_t cols, int64_t n_total, int64_t ld, const double* rs, const double* cs,
                         const double* g, double* out, int64_t ldo, cudaStream_t s);
+// <Ac, Bc>_F with both symmetric factors centred on the fly from their row sums r and grand sums g (device scalars);
+// rA == NULL / rB == NULL: that factor is taken as it is; B == NULL: sum of Ac
+int kmg_ew_centered_dot(const double* A, int64_t lda, const double* rA, const double* gA, const double* B, int64_t ldb, const double* rB,
+                        const double* gB, int64_t n, double* partial, double* result, cudaStream_t s);
+// second stage of the epilogue row statistics (epi_ops.cuh): out[r] = sum_chunk partial[r][chunk], fixed order
+int kmg_ew_partial_rows_reduce(const double* partial, int64_t rows, int64_t n_chunks, double* out, cudaStream_t s);
+int kmg_ew_vec_sum(const double* v, int64_t n, double* out, cudaStream_t s);
+int kmg_ew_vec_dot(const double* a, const double* b, int64_t n, double* out, cudaStream_t s);
+int kmg_ew_row_wsums(const double* K, int64_t rows, int64_t cols, int64_t ld, const double* w, double* out, cudaStream_t s);
+int kmg_ew_gather_vec(const double* v, const int64_t* idx, int64_t m, double* out, cudaStream_t s);
+// out = [out +] u * normalised(K), power / normalisation of the last term: the stored-Gram form of the fused accumulate epilogue
+int kmg_ew_accumulate(const double* K, int64_t ldk, const double* sd, const EpiOps* e, int64_t n, double* out, int64_t ldo, cudaStream_t s);

@@ -3,6 +3,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "epi_ops.cuh"
+
 #define KMG_OUT_S32 0
 #define KMG_OUT_F64 1
 #define KMG_MAX_PARTS 8  // power of two
@@ -33,6 +35,7 @@ struct GramI8Args {
     int n_parts, part;
     const int64_t* part_row0;  // host: n_parts + 1 boundaries, multiples of 256 except the last (= n)
     void* const* part_out;     // host: device base pointer of every part's block-row buffer (row stride ldo)
+    const EpiOps* epi;         // optional fused ALIGNF / NLCK steps (epi_ops.cuh): plain fp64 block, CTA-pair kernel
 };
 
 // 1 when part `a` of `g` (boundaries part_row0, multiples of 256) computes tile (I, J) of the global 256 x 256 tile grid,

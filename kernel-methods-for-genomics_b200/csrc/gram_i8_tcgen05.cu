@@ -20,6 +20,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdlib.h>
+#include <string.h>
 
 #include <algorithm>
 #include <array>
@@ -28,6 +29,7 @@
 #include <tuple>
 #include <vector>
 
+#include "epi_ops.cuh"
 #include "gram_i8.h"
 #include "kmg_common.cuh"
 #include "ptx_sm100.cuh"
@@ -103,14 +105,37 @@ __device__ __forceinline__ double u32_to_f64(uint32_t v) {
     return __hiloint2double((int)hi, (int)(w << 20));
 }
 
-template <bool INT_CVT>
+template <bool INT_CVT, bool FUSED = false>
 __device__ __forceinline__ void store_chunk(const KernelParams& p, const uint32_t (&v)[32], uint32_t* stage /*4 KB*/,
-                                            int lane, int64_t row_base, int64_t col0, void* out_t) {
+                                            int lane, int64_t row_base, int64_t col0, void* out_t, const EpiOps* ep = nullptr) {
     const bool mirror = out_t != nullptr;
     const int64_t ncol = (p.cols - col0 < 32) ? (p.cols - col0) : 32;  // warp-uniform, > 0
     int64_t nrow = p.rows - row_base;
     if (nrow > 32) nrow = 32;
     if (nrow <= 0) return;  // warp-uniform
+    if (FUSED && (ep->row_sum_partial != nullptr || ep->row_wsum_partial != nullptr)) {
+        // Row statistics of the chunk straight from the accumulators: after tcgen05.ld thread t holds row t, so the sums
+        // over the chunk's 32 columns need no communication.  Values as they are stored (normalised if sd is given).
+        const int64_t row = row_base + lane;
+        if (row < p.rows) {
+            const double sr = p.sd_rows != nullptr ? p.sd_rows[row] : 1.0;
+            double s = 0.0, w = 0.0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                if (j < ncol) {
+                    double d = u32_to_f64<INT_CVT>(v[j]);
+                    if (p.sd_rows != nullptr) {
+                        d = __ddiv_rn(d, __dmul_rn(sr, p.sd_cols[col0 + j]));
+                        if (p.row_index0 + row == p.col_index0 + col0 + j) d = 1.0;
+                    }
+                    s += d;
+                    if (ep->row_wsum_partial != nullptr) w += __dmul_rn(d, ep->w_cols[col0 + j]);
+                }
+            }
+            if (ep->row_sum_partial != nullptr) ep->row_sum_partial[row * ep->n_chunks + (col0 >> 5)] = s;
+            if (ep->row_wsum_partial != nullptr) ep->row_wsum_partial[row * ep->n_chunks + (col0 >> 5)] = w;
+        }
+    }
     {
         uint4* srow = reinterpret_cast<uint4*>(stage + lane * 32);
 #pragma unroll
@@ -128,7 +153,7 @@ __device__ __forceinline__ void store_chunk(const KernelParams& p, const uint32_
     // Only in the kernels whose epilogue is on the critical path (INT_CVT == false: small D, or the serial-epilogue
     // variants): under a long main loop the leaner, burstier store stream measurably slows the MMA pipeline
     // (25k x 200k block-row: 54.3 ms with the general path, 56.5 ms with this one), and the epilogue is hidden anyway.
-    if (!INT_CVT && nrow == 32 && ncol == 32 && !norm && (p.ldo & 1) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0) {
+    if (!FUSED && !INT_CVT && nrow == 32 && ncol == 32 && !norm && (p.ldo & 1) == 0 && (reinterpret_cast<uintptr_t>(p.out) & 15) == 0) {
         const uint32_t* src = stage + half * 32 + ((l16 & 1) << 1);
         const int cl = l16 >> 1;
         if (p.out_dtype == KMG_OUT_S32) {
@@ -211,6 +236,17 @@ __device__ __forceinline__ void store_chunk(const KernelParams& p, const uint32_
                     if (grow == gcol + 1) d1 = 1.0;
                 }
                 double* dst = base + (row_base + rr) * p.ldo + col;
+                if (FUSED) {  // sum_m u_m K_m, power, normalisation of the combination (epi_ops.cuh)
+                    const int64_t grow = p.row_index0 + row_base + rr, gcol = p.col_index0 + col;
+                    const bool nrm = ep->post_sd_rows != nullptr;
+                    const double psr = nrm ? ep->post_sd_rows[row_base + rr] : 1.0;
+                    const double prev0 = ep->accumulate == 2 ? dst[0] : 0.0;
+                    d0 = epi_finish(*ep, d0, prev0, grow == gcol, psr, nrm ? ep->post_sd_cols[col] : 1.0);
+                    if (ok == 2) {
+                        const double prev1 = ep->accumulate == 2 ? dst[1] : 0.0;
+                        d1 = epi_finish(*ep, d1, prev1, grow == gcol + 1, psr, nrm ? ep->post_sd_cols[col + 1] : 1.0);
+                    }
+                }
                 if (ok == 2 && vec) *reinterpret_cast<double2*>(dst) = make_double2(d0, d1);
                 else { dst[0] = d0; if (ok == 2) dst[1] = d1; }
             }
@@ -467,10 +503,10 @@ struct Cfg2 {
     static constexpr uint32_t SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256 + NUM_EPI_WARPS * EPI_STAGE_WORDS * 4;
 };
 
-template <bool INT_CVT, bool TMA_MIRROR>
+template <bool INT_CVT, bool TMA_MIRROR, bool FUSED = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gram_i8_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                    const __grid_constant__ CUtensorMap tmT, const KernelParams p) {
+                    const __grid_constant__ CUtensorMap tmT, const KernelParams p, const __grid_constant__ EpiOps epi) {
     using C = Cfg2;
     extern __shared__ uint8_t smem_raw[];
     // 1024-B alignment by offsetting the __shared__ symbol (keeps the address space known to the compiler: LDS/STS, not generic LD/ST)
@@ -599,7 +635,7 @@ gram_i8_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                     store_chunk<INT_CVT>(p, v, st, lane, row_base, col0, nullptr);
                     if (mirror != nullptr) tma_mirror_chunk<INT_CVT>(p, v, st, lane, row_base, col0, &tmT);
                 } else {
-                    store_chunk<INT_CVT>(p, v, st, lane, row_base, col0, mirror);
+                    store_chunk<INT_CVT, FUSED>(p, v, st, lane, row_base, col0, mirror, &epi);
                 }
             }
             ptx::tcgen05_fence_before();
@@ -834,13 +870,17 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const KernelParams& p
     return KMG_OK;
 }
 
-template <bool INT_CVT, bool TMA_MIRROR>
-int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmT, const KernelParams& p, int sms, cudaStream_t stream) {
+template <bool INT_CVT, bool TMA_MIRROR, bool FUSED = false>
+int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmT, const KernelParams& p, int sms, cudaStream_t stream,
+                const EpiOps* epi = nullptr) {
+    EpiOps e;
+    memset(&e, 0, sizeof(e));
+    if (epi != nullptr) e = *epi;
     static bool attr_set[64] = {};
     int dev = 0;
     KMG_CUDA_CHECK(cudaGetDevice(&dev));
     if (!attr_set[dev & 63]) {
-        KMG_CUDA_CHECK(cudaFuncSetAttribute(gram_i8_2cta_kernel<INT_CVT, TMA_MIRROR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg2::SMEM_BYTES));
+        KMG_CUDA_CHECK(cudaFuncSetAttribute(gram_i8_2cta_kernel<INT_CVT, TMA_MIRROR, FUSED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg2::SMEM_BYTES));
         attr_set[dev & 63] = true;
     }
     int clusters = sms / 2;
@@ -860,7 +900,7 @@ int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMa
     attr[1].val.cooperative = (p.wave_counter != nullptr && coop_enabled()) ? 1 : 0;
     cfg.attrs = attr;
     cfg.numAttrs = 2;
-    KMG_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gram_i8_2cta_kernel<INT_CVT, TMA_MIRROR>, tmA, tmB, tmT, p));
+    KMG_CUDA_CHECK(cudaLaunchKernelEx(&cfg, gram_i8_2cta_kernel<INT_CVT, TMA_MIRROR, FUSED>, tmA, tmB, tmT, p, e));
     return KMG_OK;
 }
 
@@ -1009,6 +1049,15 @@ int kmg_gram_i8_launch(const GramI8Args* a, cudaStream_t stream) {
     p.hint_a = (hint_mode & 1) ? ptx::L2_EVICT_LAST : ptx::L2_EVICT_NORMAL;   // bit 0: the band's A panels stay
     p.hint_b = (hint_mode & 2) ? ptx::L2_EVICT_FIRST : ptx::L2_EVICT_NORMAL;  // bit 1: the B panels stream through
     // FP64-pipe instructions stall behind a saturated tensor pipe: integer conversion once the main loop dominates
+    if (a->epi != nullptr && epi_active(*a->epi)) {
+        // fused ALIGNF / NLCK steps: a separate kernel variant, so the plain variants carry none of this code
+        KMG_REQUIRE(pair && a->out_dtype == KMG_OUT_F64 && !a->symmetric && !a->mirror_all && !sharded, KMG_ERR_ARG,
+                    "gram_i8: fused epilogue steps need the CTA-pair kernel, fp64 output and a plain block");
+        KMG_REQUIRE(!(a->epi->row_sum_partial || a->epi->row_wsum_partial) || a->epi->n_chunks >= (a->cols + 31) / 32, KMG_ERR_ARG,
+                    "gram_i8: n_chunks >= ceil(cols / 32)");
+        KMG_REQUIRE(!a->epi->row_wsum_partial || a->epi->w_cols, KMG_ERR_ARG, "gram_i8: weighted row partial sums need w_cols");
+        return launch_pair<false, false, true>(tmA, tmB, tmA, p, sms, stream, a->epi);
+    }
     if (pair) {
         // Mirror stores through the TMA engine (cp.async.bulk.tensor) whenever the destination allows a tensor map: one
         // destination (not the multi-destination single-launch sharded variant), 16-byte aligned base and row pitch.

@@ -151,8 +151,13 @@ int d2h_rows(double* dst, int64_t ldk, const void* src_v, int src_elem, int64_t 
         const int64_t nr = std::min<int64_t>(chunk_rows, rows - r);
         if (fut[slot].valid() && fut[slot].get() != 0) err = KMG_ERR_CUDA;
         if (err) break;
-        KMG_CUDA_CHECK(cudaMemcpyAsync(g_ring.buf[slot], src + (size_t)r * row_bytes, (size_t)nr * row_bytes, cudaMemcpyDeviceToHost, s));
-        KMG_CUDA_CHECK(cudaEventRecord(g_ring.ev[slot], s));
+        // no early return from here on: copy threads of earlier slots may still be writing into `dst`
+        if (cudaMemcpyAsync(g_ring.buf[slot], src + (size_t)r * row_bytes, (size_t)nr * row_bytes, cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+            cudaEventRecord(g_ring.ev[slot], s) != cudaSuccess) {
+            kmg_set_error("device-to-host copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+            err = KMG_ERR_CUDA;
+            break;
+        }
         const char* stage = reinterpret_cast<const char*>(g_ring.buf[slot]);
         cudaEvent_t ev = g_ring.ev[slot];
         double* d0 = dst + r * ldk;
@@ -345,6 +350,14 @@ int kmg_hl_build_to_host(int64_t nr, int64_t nc, bool symmetric, BlockFn fn, voi
     // streamed: two device buffers; the GPU builds block b+1 while block b drains to the host
     DevBuf buf[2];
     cudaStream_t st[2] = {s0, s1};
+    // On EVERY exit -- error returns included -- nothing of this call may still be running when the buffers go back to
+    // the allocation cache (another call could be handed them while a kernel still writes) or when control returns to
+    // a caller that may free K (copy threads still writing it): both streams are synchronised and the ring is drained
+    // before `buf` is destroyed (declared after it, so destroyed first).
+    struct Quiesce {
+        cudaStream_t a, b;
+        ~Quiesce() { cudaStreamSynchronize(a); cudaStreamSynchronize(b); ring_drain(); }
+    } quiesce{s0, s1};
     for (int i = 0; i < 2; ++i)
         if ((rc = buf[i].alloc((size_t)br * nc * esz))) return rc;
     const int64_t nblocks = (nr + br - 1) / br;

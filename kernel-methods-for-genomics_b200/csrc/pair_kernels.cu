@@ -24,6 +24,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+#include <string.h>
 
 #include "gram_i8.h"
 #include "kmg_common.cuh"
@@ -44,10 +45,15 @@ struct OutSpec {
     const double* sd_cols;
     int64_t rows, cols, row_index0, col_index0;
     int symmetric;
+    int epi;   // any of the fused steps of `e` active
+    EpiOps e;
 };
 
 OutSpec make_out(const PairBlock* b) {
     OutSpec o;
+    memset(&o.e, 0, sizeof(o.e));
+    o.epi = 0;
+    if (b->epi != nullptr) { o.e = *b->epi; o.epi = epi_active(o.e) ? 1 : 0; }
     o.out = b->out; o.ldo = b->ldo; o.out_t = b->symmetric ? b->out_t : nullptr; o.ldo_t = b->ldo_t;
     o.dtype = b->out_dtype; o.sd_rows = b->sd_rows; o.sd_cols = b->sd_cols;
     o.rows = b->rows; o.cols = b->cols; o.row_index0 = b->row_index0; o.col_index0 = b->col_index0;
@@ -75,15 +81,34 @@ __device__ __forceinline__ double finish_int(const OutSpec& o, int64_t r, int64_
     return v;
 }
 
-__device__ __forceinline__ void store_int(const OutSpec& o, int64_t r, int64_t c, int64_t raw, bool mirror) {
+// fused ALIGNF / NLCK steps on the value of entry (r, c) (block-local indices): returns what is to be stored
+__device__ __forceinline__ double apply_epi(const OutSpec& o, int64_t r, int64_t c, double v) {
+    if (!o.epi) return v;
+    const double prev = o.e.accumulate == 2 ? reinterpret_cast<const double*>(o.out)[r * o.ldo + c] : 0.0;
+    const bool nrm = o.e.post_sd_rows != nullptr;
+    return epi_finish(o.e, v, prev, o.row_index0 + r == o.col_index0 + c, nrm ? o.e.post_sd_rows[r] : 1.0, nrm ? o.e.post_sd_cols[c] : 1.0);
+}
+
+// cosine normalisation of an fp64 kernel value (weighted degree: the diagonal has already been set)
+__device__ __forceinline__ double finish_f64(const OutSpec& o, int64_t r, int64_t c, double v) {
+    if (o.sd_rows != nullptr) {
+        v = __ddiv_rn(v, __dmul_rn(o.sd_rows[r], o.sd_cols[c]));   // normalize_K (kernels.py:408-414)
+        if (o.row_index0 + r == o.col_index0 + c) v = 1.0;
+    }
+    return v;
+}
+
+// returns the fp64 value stored (0 for the s32 output, which takes no fused steps)
+__device__ __forceinline__ double store_int(const OutSpec& o, int64_t r, int64_t c, int64_t raw, bool mirror) {
     if (o.dtype == KMG_OUT_S32) {
         reinterpret_cast<int32_t*>(o.out)[r * o.ldo + c] = (int32_t)raw;
         if (mirror) reinterpret_cast<int32_t*>(o.out_t)[c * o.ldo_t + r] = (int32_t)raw;
-    } else {
-        const double v = finish_int(o, r, c, raw);
-        reinterpret_cast<double*>(o.out)[r * o.ldo + c] = v;
-        if (mirror) reinterpret_cast<double*>(o.out_t)[c * o.ldo_t + r] = v;
+        return 0.0;
     }
+    const double v = apply_epi(o, r, c, finish_int(o, r, c, raw));
+    reinterpret_cast<double*>(o.out)[r * o.ldo + c] = v;
+    if (mirror) reinterpret_cast<double*>(o.out_t)[c * o.ldo_t + r] = v;
+    return v;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -269,7 +294,9 @@ mismatch_kernel(const uint32_t* __restrict__ prow, const uint32_t* __restrict__ 
     const SeqPlanes x = kmg_load_planes(prow, live ? r : 0);
     const SeqPlanes y = kmg_load_planes(pcol, live ? c : 0);
     const int64_t raw = mismatch_pair<K, B, NW>(x, y, mp, vmask);
-    if (live) store_int(o, r, c, raw, cls == 1);
+    double v = 0.0;
+    if (live) v = store_int(o, r, c, raw, cls == 1);
+    if (o.epi && r < o.rows) epi_row_partial_warp(o.e, r, c0, v, live, threadIdx.x & 31);  // warp-uniform: r, c0
 }
 
 template <int K, int B, int NW>
@@ -382,9 +409,12 @@ wd_kernel(const uint32_t* __restrict__ prow, const uint32_t* __restrict__ pcol, 
 #pragma unroll
     for (int j = 0; j < WD_PPT; ++j) {
         const int64_t c = c0 + tc + 32 * j;
+        const bool live = row_ok && c < o.cols;
         if (o.row_index0 + r == o.col_index0 + c) acc[j] = wp.diag;
-        if (row_ok && c < o.cols) reinterpret_cast<double*>(o.out)[r * o.ldo + c] = acc[j];
+        if (live && (o.sd_rows != nullptr || o.epi)) acc[j] = apply_epi(o, r, c, finish_f64(o, r, c, acc[j]));
+        if (live) reinterpret_cast<double*>(o.out)[r * o.ldo + c] = acc[j];
         if (cls == 1) tile[tr][tc + 32 * j] = acc[j];
+        if (o.epi && row_ok && c0 + 32 * j < o.cols) epi_row_partial_warp(o.e, r, c0 + 32 * j, acc[j], live, tc);  // warp-uniform test
     }
     if (cls == 1) {  // mirror through shared memory so each column receives 8 consecutive doubles
         __syncthreads();
@@ -474,7 +504,9 @@ wds_kernel(const uint32_t* __restrict__ prow, const uint32_t* __restrict__ pcol,
         }
         c_t = __dadd_rn(c_t, __dmul_rn(wp.beta[k - 1], c_st));
     }
+    if (live && (o.sd_rows != nullptr || o.epi)) c_t = apply_epi(o, r, c, finish_f64(o, r, c, c_t));
     if (live) reinterpret_cast<double*>(o.out)[r * o.ldo + c] = c_t;
+    if (o.epi && r < o.rows) epi_row_partial_warp(o.e, r, c0, c_t, live, tc);
     if (cls == 1) {
         tile[tr][tc] = c_t;
         __syncthreads();
@@ -491,6 +523,13 @@ int check_block(const PairBlock* b) {
     if (b->symmetric) {
         KMG_REQUIRE(b->rows == b->cols && b->row_index0 == b->col_index0 && b->out_t != nullptr, KMG_ERR_ARG,
                     "symmetric mode needs a square diagonal block and a mirror destination");
+    }
+    if (b->epi != nullptr && epi_active(*b->epi)) {
+        KMG_REQUIRE(b->out_dtype == KMG_OUT_F64, KMG_ERR_ARG, "fused epilogue steps need the fp64 output");
+        KMG_REQUIRE(!(b->epi->row_sum_partial || b->epi->row_wsum_partial) || (!b->symmetric && b->epi->n_chunks >= (b->cols + 31) / 32), KMG_ERR_ARG,
+                    "row partial sums need a plain (non-symmetric) block and n_chunks >= ceil(cols / 32)");
+        KMG_REQUIRE(!b->epi->row_wsum_partial || b->epi->w_cols, KMG_ERR_ARG, "weighted row partial sums need w_cols");
+        KMG_REQUIRE((b->epi->post_sd_rows == nullptr) == (b->epi->post_sd_cols == nullptr), KMG_ERR_ARG, "post_sd_rows and post_sd_cols go together");
     }
     return KMG_OK;
 }
@@ -618,7 +657,7 @@ int kmg_wd_launch(const PairBlock* b, int d, cudaStream_t stream) {
     if (rc) return rc;
     KMG_REQUIRE(d >= 1 && d <= 127, KMG_ERR_ARG, "weighted degree: need 1 <= d <= 127 (d=%d)", d);
     KMG_REQUIRE(b->out_dtype == KMG_OUT_F64, KMG_ERR_ARG, "weighted degree Gram is fp64 (kernels.py:74-81)");
-    KMG_REQUIRE(b->sd_rows == nullptr, KMG_ERR_ARG, "weighted degree: no fused normalisation");
+    KMG_REQUIRE((b->sd_rows == nullptr) == (b->sd_cols == nullptr), KMG_ERR_ARG, "weighted degree: sd_rows and sd_cols go together");
     if (b->rows == 0 || b->cols == 0) return KMG_OK;
     WdParams wp;
     wp.d = d; wp.L = b->L;
@@ -641,7 +680,7 @@ int kmg_wds_launch(const PairBlock* b, int d, int S, cudaStream_t stream) {
     if (rc) return rc;
     KMG_REQUIRE(d >= 1 && d <= 127, KMG_ERR_ARG, "weighted degree with shifts: need 1 <= d <= 127 (d=%d)", d);
     KMG_REQUIRE(S >= 0 && S <= 7, KMG_ERR_UNSUPPORTED, "weighted degree with shifts: 0 <= S <= 7 supported (S=%d)", S);
-    KMG_REQUIRE(b->out_dtype == KMG_OUT_F64 && b->sd_rows == nullptr, KMG_ERR_ARG, "weighted degree with shifts Gram is raw fp64");
+    KMG_REQUIRE(b->out_dtype == KMG_OUT_F64 && (b->sd_rows == nullptr) == (b->sd_cols == nullptr), KMG_ERR_ARG, "weighted degree with shifts Gram is fp64");
     if (b->rows == 0 || b->cols == 0) return KMG_OK;
     WdsParams wp;
     wp.d = d; wp.S = S; wp.L = b->L;

@@ -4,6 +4,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "epi_ops.cuh"
+
 struct PairBlock {
     const uint32_t* planes_rows;  // bit-planes of the block's row sequences (device, 8 words each)
     const uint32_t* planes_cols;
@@ -18,6 +20,8 @@ struct PairBlock {
     int64_t ldo_t;
     const double* sd_rows;           // optional cosine normalisation (sqrt of the raw diagonal)
     const double* sd_cols;
+    const EpiOps* epi;               // optional fused ALIGNF / NLCK steps (epi_ops.cuh); fp64 output only; row partials need a
+                                     // plain (non-symmetric) block whose column origin is a multiple of 32
 };
 
 #define KMG_MM_MAX_M 3

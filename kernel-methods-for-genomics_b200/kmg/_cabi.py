@@ -54,6 +54,9 @@ PROTOTYPES = {
     "kmg_combine_host": (_i32, [_vp, _i32, _i64, _vp, _i32, _i32, _vp]),
     "kmg_alignf_stats_host": (_i32, [_vp, _i32, _i64, _vp, _i64, _vp, _vp, _vp]),
     "kmg_nlck_grad_host": (_i32, [_vp, _i32, _i64, _vp, _vp, _i32, _vp]),
+    "kmg_alignf_fused_host": (_i32, [_vp, _i64, _i32, _i32, _vp, _i32, _vp, _i64, _vp, _vp, _vp, _vp]),
+    "kmg_combine_fused_host": (_i32, [_vp, _i64, _i32, _i32, _vp, _i32, _vp, _i32, _i32, _i32, _vp, _i64, _vp]),
+    "kmg_build_grams_dev": (_i32, [_vp, _i64, _i32, _i32, _vp, _i32, _vp, _i64, _i32, _vp]),
     "kmg_pack_dev": (_i32, [_vp, _i32, _i64, _i32, _vp, _vp, _vp]),
     "kmg_spectrum_phi_width": (_i64, [_vp, _i32]),
     "kmg_spectrum_phi_dev": (_i32, [_vp, _i64, _i32, _vp, _i32, _vp, _i64, _vp]),

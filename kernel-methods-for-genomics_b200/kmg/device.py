@@ -215,7 +215,11 @@ def la_block(planes_rows, planes_cols, L, e, d, beta, smith=0, row_index0=0, col
 
 
 def normalize_(K):
+    """normalize_K (kernels.py:398-415) in place on a device-resident Gram, including the reference's early-out: a matrix
+    whose K[0,0] is exactly 1 is returned untouched (kernels.py:404-405)."""
     n = K.shape[0]
+    if n == 0 or float(K[0, 0].item()) == 1.0:
+        return K
     sd = torch.empty(n, dtype=torch.float64, device=K.device)
     check(_cabi.lib().kmg_normalize_dev(_p(K), n, K.stride(0), _p(sd), _stream()))
     return K

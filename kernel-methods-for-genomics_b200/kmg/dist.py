@@ -105,6 +105,8 @@ def wd_block_row(planes, L, d, n, group=None):
 def mismatch_block_row(planes, L, k, m, n, normalize=True, group=None):
     from . import device as kd
     sd = kd.mismatch_diag_sqrt(planes, L, k, m) if normalize else None  # every rank computes all n diagonals: no collective
+    if sd is not None and n > 0 and float(sd[0].item()) == 1.0:
+        sd = None  # normalize_K's early-out (kernels.py:404-405): a raw K[0,0] of exactly 1 leaves the Gram unnormalised
 
     def build(r0, r1):
         return kd.mismatch_block(planes[r0:r1], planes, L, k, m, row_index0=r0,

@@ -193,3 +193,84 @@ def test_wds_golden_and_oracle(kd, kh, golden, dna):
     assert np.array_equal(kd.wds_block(planes, planes, 101, 5, 2, symmetric=True).cpu().numpy(), want)
     cc = onp.synthetic_codes(20, 37, seed=4)
     assert np.array_equal(kh.wds_gram(cc, 6, 4), onp.wds_gram(cc, 6, 4))
+
+
+# ------------------------------------------------------------------ local alignment: third, literal route
+LA_PARAM_SETS = ((11, 1, 0.5), (-11, -1, 0.5), (11, 1, 0.1), (-5.5, -0.7, 1.3))
+
+
+@pytest.mark.parametrize("smith", [0, 1])
+def test_la_256_pairs_literal_logsumexp_rtol_1e12(kh, dna, smith):
+    """Parity-unpinned kernel (the reference returns 0.0): 256 sampled pairs of real 101-bp sequences, all
+    four parameter sets, against a LITERAL log-sum-exp evaluation of the intended recursion (tests/la_literal.py: chains
+    of numpy.logaddexp, no code shared with the kernel or the oracle).  Tolerance: 1e-12 relative, per entry."""
+    from la_literal import la_pairs_logspace
+    codes, _ = dna
+    rng = np.random.default_rng(7)
+    ri, ci = rng.choice(9000, 16, replace=False), rng.choice(9000, 16, replace=False)
+    rows, cols = codes[ri], codes[ci]
+    xs, ys = np.repeat(rows, 16, axis=0), np.tile(cols, (16, 1))       # pair p = (row p // 16, col p % 16)
+    for (e, d, beta) in LA_PARAM_SETS:
+        want = la_pairs_logspace(xs, ys, e, d, beta, smith).reshape(16, 16)
+        got = kh.la_gram(rows, e, d, beta, smith, cols=cols)           # cross-Gram: x is always the row sequence
+        assert np.all(np.isfinite(got)) and np.all(got > 0)
+        rel = np.abs(got - want) / np.abs(want)
+        assert rel.max() <= 1e-12, (smith, e, d, beta, rel.max())
+
+
+def test_config5_la_block_at_scale(kd):
+    """BASELINE config 5 shape: local alignment (affine, reference defaults e=11 d=1 beta=0.5 taken literally) on the
+    n = 20 000 synthetic problem (seed 5): a 512 x 20 000 block-row.  Size-independent properties -- the block that holds
+    the diagonal is symmetric about it and equals the symmetric-mode build, K[A,B] == K[B,A]^T across blocks (x is always
+    the sequence of smaller index, kernels.py:289-291), every value finite and positive -- and sampled tiles against the C
+    oracle at 1e-12 relative."""
+    import torch
+    n, r0, R = 20_000, 7_000, 512
+    c = onp.synthetic_codes(n, 101, seed=5)
+    planes = kd.pack(c, 0)
+    blk = kd.la_block(planes[r0:r0 + R], planes, 101, 11, 1, 0.5, 0, row_index0=r0)
+    assert bool(torch.isfinite(blk).all()) and float(blk.min()) > 0.0
+    dg = blk[:, r0:r0 + R]
+    assert torch.equal(dg, dg.t())
+    sym = kd.la_block(planes[r0:r0 + R], planes[r0:r0 + R], 101, 11, 1, 0.5, 0, row_index0=r0, col_index0=r0, symmetric=True)
+    assert torch.equal(sym, dg)
+    other = kd.la_block(planes[1000:1128], planes[r0:r0 + R], 101, 11, 1, 0.5, 0, row_index0=1000, col_index0=r0)
+    assert torch.equal(other.t(), blk[:, 1000:1128])
+    other = kd.la_block(planes[19_000:19_128], planes[r0:r0 + R], 101, 11, 1, 0.5, 0, row_index0=19_000, col_index0=r0)
+    assert torch.equal(other.t(), blk[:, 19_000:19_128])
+    rng = np.random.default_rng(11)
+    for _ in range(6):
+        a, b = int(rng.integers(0, R - 8)), int(rng.integers(0, n - 32))
+        want = oc.la_block(c[r0 + a:r0 + a + 8], c[b:b + 32], 11, 1, 0.5, 0, r0 + a, b)
+        got = blk[a:a + 8, b:b + 32].cpu().numpy()
+        assert np.all(np.abs(got - want) <= LA_RTOL * np.abs(want)), (a, b)
+
+
+def test_config4_wd_full_blockrow_at_scale(kd):
+    """BASELINE config 4 at the benchmark's unit: WD d=10, one 12 500 x 100 000 block-row of the synthetic 100k problem
+    (seed 4).  Properties: closed-form diagonal exactly where the indices coincide, 0 <= K <= diag, K[A,B] == K[B,A]^T
+    across blocks, the block holding the diagonal equals the symmetric-mode build, the entry histogram is a set of
+    multiples of 1/110 within rounding (beta_k c_k with d=10), and 10 random tiles == the C oracle bit for bit."""
+    import torch
+    n, r0, R = 100_000, 37_500, 12_500
+    c = onp.synthetic_codes(n, 101, seed=4)
+    planes = kd.pack(c, 0)
+    blk = kd.wd_block(planes[r0:r0 + R], planes, 101, 10, row_index0=r0)
+    diag = blk[torch.arange(R), torch.arange(r0, r0 + R)]
+    dv = 100 + (1 - 10) / 3
+    assert torch.all(diag == dv)
+    assert float(blk.min()) >= 0.0 and float(blk.max()) <= dv
+    dg = blk[:4096, r0:r0 + 4096]
+    assert torch.equal(dg, dg.t())
+    assert torch.equal(kd.wd_block(planes[r0:r0 + 4096], planes[r0:r0 + 4096], 101, 10, row_index0=r0, col_index0=r0, symmetric=True), dg)
+    for b0 in (0, 90_000):
+        other = kd.wd_block(planes[b0:b0 + 2048], planes[r0:r0 + R], 101, 10, row_index0=b0, col_index0=r0)
+        assert torch.equal(other.t(), blk[:, b0:b0 + 2048])
+    # 110 K is within a few ulps of an integer (beta_k = 2(11-k)/110): a cheap whole-block sanity check of the weights
+    frac = (blk[:2048] * 110.0)
+    assert float((frac - frac.round()).abs().max()) < 1e-9
+    rng = np.random.default_rng(13)
+    for _ in range(10):
+        a, b = int(rng.integers(0, R - 16)), int(rng.integers(0, n - 64))
+        want = oc.wd_block(c[r0 + a:r0 + a + 16], c[b:b + 64], 10, r0 + a, b)
+        assert np.array_equal(blk[a:a + 16, b:b + 64].cpu().numpy(), want), (a, b)

@@ -85,6 +85,27 @@ def test_config2_mismatch_full_9000_properties(kd, dna):
     assert np.array_equal(K[rows, cols].cpu().numpy(), want)
 
 
+def test_config2_mismatch_full_9000_sha256(kh, dna):
+    """BASELINE config 2 in full through the host C-ABI: get_mismatch_K(X, 10, 1) on all 9000 challenge sequences against
+    the SHA-256 known answer computed once by the plain-C oracle (oracle/gen_config2_kat.py -> tests/golden/
+    config2_mm10_kat.json; the reference cannot run this configuration).  Raw integers and the normalised fp64 matrix,
+    bit for bit."""
+    import hashlib
+    import json
+    import os
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "config2_mm10_kat.json")
+    if not os.path.exists(path):
+        pytest.skip("known answer not generated (python oracle/gen_config2_kat.py)")
+    kat = json.load(open(path))
+    codes, _ = dna
+    K = kh.mismatch_gram(codes, 10, 1)
+    assert hashlib.sha256(np.ascontiguousarray(K).tobytes()).hexdigest() == kat["sha256"]
+    assert float(np.trace(K)) == kat["trace"] and K[0, 1] == kat["K_0_1"] and K[4503, 8999] == kat["K_4503_8999"]
+    raw = kh.mismatch_gram(codes, 10, 1, normalize=False)
+    assert hashlib.sha256(np.ascontiguousarray(raw.astype(np.int64)).tobytes()).hexdigest() == kat["raw_sha256"]
+    assert int(raw[0, 0]) == kat["raw_0_0"] and int(np.trace(raw)) == kat["raw_trace"]
+
+
 def test_config4_wd_blockrow_properties(kd):
     """BASELINE config 4 shape: WD d=10, one 2048 x 100000 block-row of the synthetic 100k problem.  Properties:
     diagonal closed form exactly where indices coincide, bounds 0 <= K <= L-1+(1-d)/3 + eps, sampled tiles == oracle."""
