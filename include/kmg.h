@@ -68,6 +68,18 @@ int kmg_dev_download(void* h_dst, const void* d_src, int64_t bytes);
  * (KMG_HOST_POOL_BYTES, default 8 GiB; kmg_release empties it) so later results land in memory that is already mapped */
 int kmg_host_alloc(int64_t bytes, void** ptr);
 int kmg_host_free(void* ptr);
+/* How fp64 results reach host arrays that live in kmg_host_alloc blocks (others always take KMG_D2H_WIDEN):
+ *   KMG_D2H_WIDEN  narrow integer transport over PCIe (2-4 B/entry) + copy threads that widen to fp64: fastest for one
+ *                  process with many cores; every delivered byte is a CPU store.
+ *   KMG_D2H_DMA    the kernel writes fp64 on the device, the copy engine writes it straight into the (pinned) array:
+ *                  8 B/entry on the link, no CPU in the data path -- scales with the GPUs of a host.
+ *   KMG_D2H_MAPPED the kernel stores fp64 through the mapped address of the pinned array (zero copy).
+ * Default: env KMG_D2H_MODE (widen | dma | mapped), else widen; kmg/host.py picks per process by timing (auto). */
+#define KMG_D2H_WIDEN 0
+#define KMG_D2H_DMA 1
+#define KMG_D2H_MAPPED 2
+int kmg_set_d2h_mode(int mode);
+int kmg_get_d2h_mode(void);
 
 /* ---- host-buffer entry points (the reference-facing boundary) ------------------------------ */
 /* cols == NULL: symmetric Gram of `rows` (n x n, upper triangle computed and mirrored, as the

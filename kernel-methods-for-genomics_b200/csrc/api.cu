@@ -179,6 +179,9 @@ int kmg_dev_download(void* h_dst, const void* d_src, int64_t bytes) {
 int kmg_host_alloc(int64_t bytes, void** ptr) { return kmg_hl_host_alloc(bytes, ptr); }
 int kmg_host_free(void* ptr) { return kmg_hl_host_free(ptr); }
 
+int kmg_set_d2h_mode(int mode) { return kmg_hl_set_mode(mode); }
+int kmg_get_d2h_mode(void) { return kmg_hl_get_mode(); }
+
 int kmg_release(void) {
     kmg_hl_trim_pool();
     kmg_rt_flush_cache();
@@ -235,7 +238,7 @@ int kmg_spectrum_host(const uint8_t* rows, int64_t nr, const uint8_t* cols, int6
     KMG_CUDA_CHECK(cudaStreamSynchronize(s));
     kmg_trace("spectrum_host: Phi built");
     // unnormalised counts: ship the s32 accumulators, widen to double on the host side of PCIe
-    const bool s32 = (size_t)sp.nc * 4 <= kmg_hl_slot_bytes() && !getenv("KMG_D2H_F64");
+    const bool s32 = (size_t)sp.nc * 4 <= kmg_hl_slot_bytes() && !getenv("KMG_D2H_F64") && !kmg_hl_direct_fp64(K, ldk, sp.nr);
     SpectrumCtx ctx{phi_r.as<int8_t>(), pc, sp.nc, width, nullptr, nullptr, s32 ? KMG_OUT_S32 : KMG_OUT_F64};
     return kmg_hl_build_to_host(sp.nr, sp.nc, sp.symmetric, spectrum_block, &ctx, K, ldk, s32);
 }

@@ -237,7 +237,13 @@ struct HostPool {
     std::mutex mu;
     std::map<void*, size_t> live;
     std::multimap<size_t, void*> cached;
+    std::map<void*, size_t> registered;  // blocks pinned with cudaHostRegister (DMA / mapped delivery), live or cached
     size_t cached_bytes = 0;
+    void unmap(void* p, size_t sz) {
+        auto it = registered.find(p);
+        if (it != registered.end()) { cudaHostUnregister(p); registered.erase(it); }
+        munmap(p, sz);
+    }
     size_t cap() const {
         if (const char* v = getenv("KMG_HOST_POOL_BYTES")) return (size_t)atof(v);
         return (size_t)8 << 30;
@@ -245,7 +251,7 @@ struct HostPool {
     void trim(size_t keep) {
         while (cached_bytes > keep && !cached.empty()) {
             auto it = std::prev(cached.end());
-            munmap(it->second, it->first);
+            unmap(it->second, it->first);
             cached_bytes -= it->first;
             cached.erase(it);
         }
@@ -295,7 +301,67 @@ int try_narrow(const void* d_s32, int64_t count, DevBuf* narrow, int* elem, cuda
 }
 
 // out_s32: `fn` writes int32 counts (d2h_rows widens them on the host side of the link).
+
+// ---- delivery modes --------------------------------------------------------------------------------------------------
+//   widen  (0) narrow integer transport over PCIe + copy threads that widen to fp64 while writing the caller's array:
+//              2-4 B/entry on the link, but every delivered byte is a CPU store -- bound by the cores a process has
+//              (one GPU, 16 threads: ~1.2e10 entries/s; eight processes on one host share the same cores and DRAM).
+//   dma    (1) the kernel writes fp64 on the device and the copy engine writes it straight into the caller's array
+//              (result blocks from kmg_host_alloc, pinned once with cudaHostRegister): 8 B/entry on the link, no CPU
+//              in the data path -- PCIe-bound per GPU (~6.5e9 entries/s) but it scales with the number of GPUs.
+//   mapped (2) the kernel's epilogue stores fp64 through the mapped address of the same pinned block (zero copy).
+int g_mode = -1;
+int current_mode() {
+    if (g_mode < 0) {
+        const char* v = getenv("KMG_D2H_MODE");
+        g_mode = (v && (!strcmp(v, "dma") || !strcmp(v, "1"))) ? 1 : ((v && (!strcmp(v, "mapped") || !strcmp(v, "2"))) ? 2 : 0);
+    }
+    return g_mode;
+}
+
+// Is [K, K + bytes) inside a live result block?  Pins the block on first use.  Returns the device-visible address.
+bool pinned_target(const double* K, size_t bytes, void** dev_addr) {
+    std::lock_guard<std::mutex> lk(g_hostpool.mu);
+    auto it = g_hostpool.live.upper_bound(const_cast<double*>(K));
+    if (it == g_hostpool.live.begin()) return false;
+    --it;
+    char* base = static_cast<char*>(it->first);
+    const char* p = reinterpret_cast<const char*>(K);
+    if (p < base || p + bytes > base + it->second) return false;
+    if (!g_hostpool.registered.count(it->first)) {
+        if (cudaHostRegister(it->first, it->second, cudaHostRegisterPortable | cudaHostRegisterMapped) != cudaSuccess) {
+            cudaGetLastError();
+            return false;
+        }
+        g_hostpool.registered[it->first] = it->second;
+    }
+    if (dev_addr) {
+        void* d = nullptr;
+        if (cudaHostGetDevicePointer(&d, it->first, 0) != cudaSuccess) { cudaGetLastError(); return false; }
+        *dev_addr = static_cast<char*>(d) + (p - base);
+    }
+    return true;
+}
 }  // namespace
+
+int kmg_hl_set_mode(int mode) {
+    KMG_REQUIRE(mode >= 0 && mode <= 2, KMG_ERR_ARG, "d2h mode: 0 widen, 1 dma, 2 mapped");
+    if (mode == 0 && g_mode > 0) {
+        // back to the copy threads: un-pin the result blocks (measured: the widening threads write registered memory at
+        // about half the rate of plain pageable huge pages)
+        std::lock_guard<std::mutex> lk(g_hostpool.mu);
+        for (auto& kv : g_hostpool.registered) cudaHostUnregister(kv.first);
+        g_hostpool.registered.clear();
+    }
+    g_mode = mode;
+    return KMG_OK;
+}
+int kmg_hl_get_mode() { return current_mode(); }
+// true: kmg_hl_build_to_host will deliver fp64 by DMA / mapped stores into K -- the caller then asks its kernel for fp64
+bool kmg_hl_direct_fp64(const double* K, int64_t ldk, int64_t nr) {
+    if (current_mode() == 0 || nr <= 0) return false;
+    return pinned_target(K, (size_t)((nr - 1) * ldk + ldk) * sizeof(double), nullptr);
+}
 
 int kmg_hl_build_to_host(int64_t nr, int64_t nc, bool symmetric, BlockFn fn, void* ctx, double* K, int64_t ldk, bool out_s32) {
     if (nr == 0 || nc == 0) return KMG_OK;
@@ -305,6 +371,48 @@ int kmg_hl_build_to_host(int64_t nr, int64_t nc, bool symmetric, BlockFn fn, voi
     if (rc) return rc;
     int64_t br = 0;
     if ((rc = pick_block_rows(nr, nc, &br))) return rc;
+    void* mapped = nullptr;
+    const bool direct = !out_s32 && current_mode() != 0 && !(symmetric && br < nr) && pinned_target(K, (size_t)((nr - 1) * ldk + ldk) * sizeof(double), &mapped);
+    if (direct && current_mode() == 2) {
+        // zero copy: the producing kernel stores through the mapped address of the caller's (pinned) array
+        if ((rc = fn(ctx, 0, nr, mapped, ldk, symmetric ? 1 : 0, s0))) { cudaStreamSynchronize(s0); return rc; }
+        KMG_CUDA_CHECK(cudaStreamSynchronize(s0));
+        return KMG_OK;
+    }
+    if (direct) {
+        // copy engine straight into the caller's (pinned) array: row chunks so the link starts while the GPU still builds
+        const int64_t rows_cap = std::min<int64_t>(br, nr);
+        const int nchunks = symmetric ? 1 : (int)std::min<int64_t>(8, std::max<int64_t>(1, nr / 256));
+        const int64_t crow = symmetric ? nr : std::min<int64_t>(rows_cap, ((nr + nchunks - 1) / nchunks + 255) / 256 * 256);
+        DevBuf buf[2];
+        struct Quiesce2 {
+            cudaStream_t a, b;
+            ~Quiesce2() { cudaStreamSynchronize(a); cudaStreamSynchronize(b); }
+        } quiesce{s0, s1};
+        for (int i = 0; i < 2; ++i)
+            if ((rc = buf[i].alloc((size_t)crow * nc * sizeof(double)))) return rc;
+        cudaEvent_t built[2] = {}, copied[2] = {};
+        for (int i = 0; i < 2; ++i) {
+            KMG_CUDA_CHECK(cudaEventCreateWithFlags(&built[i], cudaEventDisableTiming));
+            KMG_CUDA_CHECK(cudaEventCreateWithFlags(&copied[i], cudaEventDisableTiming));
+        }
+        int c = 0;
+        for (int64_t r0 = 0; r0 < nr && rc == KMG_OK; r0 += crow, ++c) {
+            const int64_t rows = std::min<int64_t>(crow, nr - r0);
+            const int b = c & 1;
+            if (c >= 2 && cudaStreamWaitEvent(s0, copied[b], 0) != cudaSuccess) { rc = KMG_ERR_CUDA; break; }  // buffer drained
+            if ((rc = fn(ctx, r0, rows, buf[b].p, nc, symmetric ? 1 : 0, s0))) break;
+            if (cudaEventRecord(built[b], s0) != cudaSuccess || cudaStreamWaitEvent(s1, built[b], 0) != cudaSuccess ||
+                cudaMemcpy2DAsync(K + r0 * ldk, (size_t)ldk * 8, buf[b].p, (size_t)nc * 8, (size_t)nc * 8, (size_t)rows, cudaMemcpyDeviceToHost, s1) != cudaSuccess ||
+                cudaEventRecord(copied[b], s1) != cudaSuccess) {
+                kmg_set_error("build_to_host (dma): %s", cudaGetErrorString(cudaGetLastError()));
+                rc = KMG_ERR_CUDA;
+            }
+        }
+        if (rc == KMG_OK && cudaStreamSynchronize(s1) != cudaSuccess) { kmg_set_error("build_to_host (dma): copy failed"); rc = KMG_ERR_CUDA; }
+        for (int i = 0; i < 2; ++i) { cudaEventDestroy(built[i]); cudaEventDestroy(copied[i]); }
+        return rc;
+    }
     if (br >= nr) {
         // The whole block fits.  A large cross-Gram is still built in a few row chunks, all enqueued up front: the host
         // link (the slow side) starts on chunk 0 while the GPU builds the rest, and the copy threads run across chunk
@@ -420,14 +528,14 @@ int kmg_hl_host_free(void* ptr) {
     const size_t sz = it->second;
     g_hostpool.live.erase(it);
     const size_t cap = g_hostpool.cap();
-    if (sz > cap) { munmap(ptr, sz); return KMG_OK; }
+    if (sz > cap) { g_hostpool.unmap(ptr, sz); return KMG_OK; }
     g_hostpool.cached.emplace(sz, ptr);
     g_hostpool.cached_bytes += sz;
     if (g_hostpool.cached_bytes > cap) {  // evict the other blocks, largest first, keeping the one just returned
         for (auto c = g_hostpool.cached.end(); g_hostpool.cached_bytes > cap && c != g_hostpool.cached.begin();) {
             --c;
             if (c->second == ptr) continue;
-            munmap(c->second, c->first);
+            g_hostpool.unmap(c->second, c->first);
             g_hostpool.cached_bytes -= c->first;
             c = g_hostpool.cached.erase(c);
         }

@@ -19,3 +19,9 @@ size_t kmg_hl_slot_bytes();
 int kmg_hl_host_alloc(int64_t bytes, void** ptr);
 int kmg_hl_host_free(void* ptr);
 void kmg_hl_trim_pool();
+// delivery mode of the fp64 results (0 widen: narrow transport + copy threads, 1 dma: copy engine into pinned result
+// blocks, 2 mapped: kernel stores through the mapped address); default from KMG_D2H_MODE, else widen
+int kmg_hl_set_mode(int mode);
+int kmg_hl_get_mode();
+// true when kmg_hl_build_to_host will deliver fp64 straight into K (dma / mapped): the caller then builds fp64, not s32
+bool kmg_hl_direct_fp64(const double* K, int64_t ldk, int64_t nr);

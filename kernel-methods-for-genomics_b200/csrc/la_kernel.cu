@@ -30,6 +30,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "gram_i8.h"
 #include "kmg_common.cuh"
@@ -37,7 +38,8 @@
 
 namespace {
 
-constexpr int LA_THREADS = 256;
+constexpr int LA_THREADS = 128;
+constexpr int LA_YPAD = 32;  // >= LP - 1: the column index of a lane runs from -(LP-1) to L+LP-2
 
 struct LaParams {
     int L;
@@ -63,45 +65,76 @@ __device__ __forceinline__ int code_at(const SeqPlanes& s, int pos) {
     return (int)(((lo >> b) & 1u) | (((hi >> b) & 1u) << 1));
 }
 
+// The two half-warps of a warp run the same number of steps, so the shuffles use the FULL mask with a segment width of
+// LP: with the half-warp mask the compiler cannot prove the mask uniform and wraps every shuffle in MATCH.ANY / REDUX /
+// BRA.DIV (round 1: ~15 of the 153 instructions of a step, and the top stall of the loop).
 template <int LP>
-__device__ __forceinline__ double shfl_up_d(unsigned mask, double v) { return __shfl_up_sync(mask, v, 1, LP); }
+__device__ __forceinline__ double shfl_up_d(double v) { return __shfl_up_sync(0xffffffffu, v, 1, LP); }
 
-template <int LP, int RPL>
-__global__ void __launch_bounds__(LA_THREADS)
+__device__ __forceinline__ double lds_f64(uint32_t addr) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+    return v;
+}
+
+// substitution value of row q of this lane's strip against the column code the address was formed for
+template <int OFF>
+__device__ __forceinline__ double lds_f64_off(uint32_t addr) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1+%2];" : "=d"(v) : "r"(addr), "n"(OFF));
+    return v;
+}
+
+template <int LP, int RPL, int MIN_BLOCKS>
+__global__ void __launch_bounds__(LA_THREADS, MIN_BLOCKS)
 la_kernel(const uint32_t* __restrict__ prow, const uint32_t* __restrict__ pcol, const LaParams p) {
     constexpr int GROUPS = LA_THREADS / LP;  // pairs per CTA
-    __shared__ uint8_t ycode_s[GROUPS][KMG_MAX_L];
-    __shared__ double sub_s[16];
+    // column codes of y with LA_YPAD entries of the "no base" code 4 on either side: a lane that has not reached column 0
+    // yet (or is past column L-1) looks up column 4 of its substitution table -- zeros (affine) / -inf (max-plus) -- which
+    // keeps an all-zero (all -inf) state unchanged, so the step needs no "is my column valid" branch
+    __shared__ uint8_t ycode_s[GROUPS][KMG_MAX_L + 2 * LA_YPAD];
+    // Every thread owns a private copy of the substitution values of ITS rows: tab[q][y code] = sub[x code of row q][y].
+    // The address of a step is (thread base + 8 * y code); the row is an immediate offset of the load: one address
+    // computation per step instead of one per cell (FP64 instructions take two issue slots each and everything else one,
+    // so every other instruction removed from the step is a slot the FP64 pipe gets: ncu, profiles/r2_la_wd_ncu.txt).
+    extern __shared__ double tab_s[];  // [LA_THREADS][RPL][5]
     const int group = threadIdx.x / LP, gl = threadIdx.x % LP;  // group in CTA, lane in group
-    const unsigned gmask = (LP == 32) ? 0xffffffffu : (0xffffu << (16 * ((threadIdx.x & 31) >> 4)));
-    if (threadIdx.x < 16) sub_s[threadIdx.x] = p.sub[threadIdx.x];
-    __syncthreads();
     int64_t pair = (int64_t)blockIdx.x * GROUPS + group;
     const int64_t npairs = p.rows * p.cols;
     const bool in_range = pair < npairs;
-    if (!in_range) pair = npairs - 1;  // keep the half-warp alive for the collectives; its result is not stored
+    if (!in_range) pair = npairs - 1;  // keep the group alive for the shuffles; its result is not stored
     const int64_t r = pair / p.cols, c = pair % p.cols;
     const int64_t gr = p.row_index0 + r, gc = p.col_index0 + c;
     const bool skip = p.symmetric && gc < gr;  // produced by the mirror store of (c, r)
-    // a whole warp whose groups have nothing to do can leave (warp-uniform test)
-    if (__all_sync(0xffffffffu, skip || !in_range)) return;
     // kernels.py:289-291: K[i,j] is evaluated with x = row i, y = row j for j >= i, then mirrored
     const bool swap = gc < gr;
     const SeqPlanes xs = swap ? kmg_load_planes(pcol, c) : kmg_load_planes(prow, r);
     const SeqPlanes ys = swap ? kmg_load_planes(prow, r) : kmg_load_planes(pcol, c);
     const int L = p.L;
-    for (int j = gl; j < KMG_MAX_L; j += LP) ycode_s[group][j] = (uint8_t)code_at(ys, j);
-    __syncwarp();
-    int xc[RPL];
+    for (int jj = gl; jj < KMG_MAX_L + 2 * LA_YPAD; jj += LP) {
+        const int j = jj - LA_YPAD;
+        ycode_s[group][jj] = (j >= 0 && j < L) ? (uint8_t)code_at(ys, j) : (uint8_t)4;
+    }
+    double* tab = tab_s + (size_t)threadIdx.x * (RPL * 5);
+    const double pad = p.smith ? -INFINITY : 0.0;
 #pragma unroll
-    for (int q = 0; q < RPL; ++q) xc[q] = code_at(xs, (gl * RPL + q) & 127) << 2;
+    for (int q = 0; q < RPL; ++q) {
+        const int xcode = code_at(xs, (gl * RPL + q) & 127);
+#pragma unroll
+        for (int yc = 0; yc < 4; ++yc) tab[q * 5 + yc] = p.sub[xcode * 4 + yc];
+        tab[q * 5 + 4] = pad;
+    }
+    __syncthreads();
+    // a whole warp whose groups have nothing to do can leave (warp-uniform test, after the only block-wide barrier)
+    if (__all_sync(0xffffffffu, skip || !in_range)) return;
+    const uint32_t tab_base = (uint32_t)__cvta_generic_to_shared(tab);
+    const uint8_t* ycol = &ycode_s[group][LA_YPAD - gl];  // ycol[t] = code of this lane's column at step t
 
     const int last_lane = (L - 1) / RPL, last_q = (L - 1) % RPL;
     const int steps = L + LP - 1;
     double result = 0.0;
 
-    // Per cell the state is kept as the sums the recursion actually consumes (rows of a lane's strip), plus M and X of
-    // the strip's bottom row for the lane below:
+    // Per cell the state is kept as the sums the recursion actually consumes (rows of a lane's strip):
     //   T = M + X       (Y [i,j] = e^{bd} T[i,j-1] + e^{be} Y[i,j-1])
     //   S = T + Y       (M [i,j] = e^{b s} (1 + S[i-1,j-1]))
     //   U = M + X2      (X2[i,j] = U[i-1,j];  Y2[i,j] = U[i,j-1] + Y2[i,j-1];  result = ln(1 + U + Y2))
@@ -113,54 +146,72 @@ la_kernel(const uint32_t* __restrict__ prow, const uint32_t* __restrict__ pcol, 
         double T[RPL], Y[RPL], U[RPL], Y2[RPL], S[RPL];
 #pragma unroll
         for (int q = 0; q < RPL; ++q) T[q] = Y[q] = U[q] = Y2[q] = S[q] = 0.0;
-        double bM = 0.0, bX = 0.0;  // M, X of the strip's bottom row
+        // What the lane below needs from this lane's bottom row: X of ITS first row at the same column,
+        // X[i+1,j] = e^{bd} M[i,j] + e^{be} X[i,j] -- formed here, so one value travels instead of two -- plus S and U.
+        double xdown = 0.0;
         double dS = 0.0;            // S of the row above the strip, previous column
         int E = 0;                  // stored = true * 2^-E
         double one_s = 1.0;
+        double tot = 1.0;           // (1 + U + Y2)[row L-1 of this lane's strip, column L-1], scaled by 2^-Etot
+        int Etot = 0;
         const double ed = p.ed, ee = p.ee;
+        // The first lane of a group has no lane above: what its shuffles return (its own values) must count as zero.
+        // Folded into the arithmetic that consumes them (a multiply-add by z0 instead of an add): no select instructions.
+        const double z0 = gl == 0 ? 0.0 : 1.0;
         int until_check = p.check_every;
 #pragma unroll 1
         for (int t = 0; t < steps; ++t) {
-            // bottom row of the lane above, as computed in the previous step (= this lane's column j)
-            double uM = shfl_up_d<LP>(gmask, bM);
-            double uX = shfl_up_d<LP>(gmask, bX);
-            double uS = shfl_up_d<LP>(gmask, S[RPL - 1]);
-            double uU = shfl_up_d<LP>(gmask, U[RPL - 1]);
-            if (gl == 0) uM = uX = uS = uU = 0.0;
-            const int j = t - gl;  // 0-based column
-            if (j >= 0 && j < L) {
-                const int yc = ycode_s[group][j];
-                double aM = uM, aX = uX, aU = uU;  // "up"   : (i-1, j)
-                double gS = dS;                    // "diag" : (i-1, j-1)
+            const double uX = shfl_up_d<LP>(xdown);        // X of this strip's first row at this lane's column
+            const double uS = shfl_up_d<LP>(S[RPL - 1]);
+            const double uU = shfl_up_d<LP>(U[RPL - 1]);
+            const uint32_t col_addr = tab_base + 8u * ycol[t];
+            double aM = 0.0, aX = 0.0, aU = 0.0;           // "up"   : (i-1, j), set by the cell above
+            double gS = dS;                                // "diag" : (i-1, j-1)
 #pragma unroll
-                for (int q = 0; q < RPL; ++q) {
-                    const double a = sub_s[xc[q] | yc];
-                    const double lT = T[q], lY = Y[q], lU = U[q], lY2 = Y2[q], lS = S[q];  // "left": (i, j-1)
-                    const double nM = a * (one_s + gS);
-                    const double nX = ed * aM + ee * aX;
-                    const double nY = ed * lT + ee * lY;
-                    const double nY2 = lU + lY2;
-                    const double nU = nM + aU;
-                    const double nT = nM + nX;
-                    gS = lS;
-                    aM = nM; aX = nX; aU = nU;
-                    T[q] = nT; Y[q] = nY; U[q] = nU; Y2[q] = nY2; S[q] = nT + nY;
+            for (int q = 0; q < RPL; ++q) {
+                double a;
+                switch (q) {  // the row is an immediate offset of the load
+                    case 0: a = lds_f64_off<0>(col_addr); break;
+                    case 1: a = lds_f64_off<40>(col_addr); break;
+                    case 2: a = lds_f64_off<80>(col_addr); break;
+                    case 3: a = lds_f64_off<120>(col_addr); break;
+                    case 4: a = lds_f64_off<160>(col_addr); break;
+                    case 5: a = lds_f64_off<200>(col_addr); break;
+                    case 6: a = lds_f64_off<240>(col_addr); break;
+                    case 7: a = lds_f64_off<280>(col_addr); break;
+                    case 8: a = lds_f64_off<320>(col_addr); break;
+                    case 9: a = lds_f64_off<360>(col_addr); break;
+                    case 10: a = lds_f64_off<400>(col_addr); break;
+                    case 11: a = lds_f64_off<440>(col_addr); break;
+                    default: a = lds_f64_off<480>(col_addr); break;
                 }
-                bM = aM; bX = aX;
-                dS = uS;
+                const double lT = T[q], lY = Y[q], lU = U[q], lY2 = Y2[q], lS = S[q];  // "left": (i, j-1)
+                const double nM = q == 0 ? a * fma(z0, gS, one_s) : a * (one_s + gS);
+                const double nX = q == 0 ? z0 * uX : ed * aM + ee * aX;
+                const double nY = ed * lT + ee * lY;
+                const double nY2 = lU + lY2;
+                const double nU = q == 0 ? fma(z0, uU, nM) : nM + aU;
+                const double nT = nM + nX;
+                gS = lS;
+                aM = nM; aX = nX; aU = nU;
+                T[q] = nT; Y[q] = nY; U[q] = nU; Y2[q] = nY2; S[q] = nT + nY;
             }
-            if (t == L - 1 + last_lane && gl == last_lane) {
-                // cell (n_x, n_y): this lane's row last_q at column L-1
+            xdown = ed * aM + ee * aX;
+            dS = uS;
+            const int j = t - gl;  // 0-based column of this lane
+            if (j == L - 1) {
+                // column n_y of this lane's rows: keep the cell of row last_q (only lane last_lane's is the result)
                 double u = U[0], y2 = Y2[0];
 #pragma unroll
                 for (int q = 1; q < RPL; ++q)
                     if (q == last_q) { u = U[q]; y2 = Y2[q]; }
-                const double tot = (one_s + u) + y2;
-                result = p.inv_beta * (log(tot) + (double)E * 0.6931471805599453094);
+                tot = (one_s + u) + y2;
+                Etot = E;
             }
             if (--until_check == 0) {
                 until_check = p.check_every;
-                // ---- group-wide power-of-two rescale (exact)
+                // ---- group-wide power-of-two rescale (exact).  Lanes past their last column hold values nobody reads:
+                // they stay out of the maximum (they may have overflowed) but are scaled along with the rest.
                 int hi = 0;
 #pragma unroll
                 for (int q = 0; q < RPL; ++q) {
@@ -168,7 +219,11 @@ la_kernel(const uint32_t* __restrict__ prow, const uint32_t* __restrict__ pcol, 
                     hi = max(hi, __double2hiint(U[q]));
                     hi = max(hi, __double2hiint(Y2[q]));
                 }
-                hi = __reduce_max_sync(gmask, hi);
+                hi = max(hi, __double2hiint(xdown));
+                if (j >= L) hi = 0;
+                // maximum over the LP lanes of the group: full-mask butterfly inside segments of LP lanes
+#pragma unroll
+                for (int o = LP / 2; o > 0; o >>= 1) hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o, LP));
                 const int ex = (hi >> 20) - 1023;  // exponent of the largest live value (all values >= 0)
                 if (ex > 64) {                     // uniform within the group
                     const double sc = __hiloint2double((1023 - ex) << 20, 0);  // 2^-ex
@@ -176,12 +231,13 @@ la_kernel(const uint32_t* __restrict__ prow, const uint32_t* __restrict__ pcol, 
                     for (int q = 0; q < RPL; ++q) {
                         T[q] *= sc; Y[q] *= sc; U[q] *= sc; Y2[q] *= sc; S[q] *= sc;
                     }
-                    bM *= sc; bX *= sc; dS *= sc;
+                    xdown *= sc; dS *= sc;
                     E += ex;
                     one_s = (E < 1000) ? __hiloint2double((1023 - E) << 20, 0) : 0.0;  // 2^-E (negligible beyond)
                 }
             }
         }
+        if (gl == last_lane) result = p.inv_beta * (log(tot) + (double)Etot * 0.6931471805599453094);
     } else {
         // ---------------- Smith_Waterman (max-plus), log space: T = max(M, X), S = max(T, Y), U = max(M, X2)
         const double NI = -INFINITY;
@@ -189,44 +245,43 @@ la_kernel(const uint32_t* __restrict__ prow, const uint32_t* __restrict__ pcol, 
 #pragma unroll
         for (int q = 0; q < RPL; ++q) T[q] = Y[q] = U[q] = Y2[q] = S[q] = NI;
         double bM = NI, bX = NI, dS = NI;
+        double best = 0.0;
         const double bd = p.bd, be = p.be;
 #pragma unroll 1
         for (int t = 0; t < steps; ++t) {
-            double uM = shfl_up_d<LP>(gmask, bM);
-            double uX = shfl_up_d<LP>(gmask, bX);
-            double uS = shfl_up_d<LP>(gmask, S[RPL - 1]);
-            double uU = shfl_up_d<LP>(gmask, U[RPL - 1]);
+            double uM = shfl_up_d<LP>(bM);
+            double uX = shfl_up_d<LP>(bX);
+            double uS = shfl_up_d<LP>(S[RPL - 1]);
+            double uU = shfl_up_d<LP>(U[RPL - 1]);
             if (gl == 0) uM = uX = uS = uU = NI;
-            const int j = t - gl;
-            if (j >= 0 && j < L) {
-                const int yc = ycode_s[group][j];
-                double aM = uM, aX = uX, aU = uU;
-                double gS = dS;
+            const double* col = tab + ycol[t];
+            double aM = uM, aX = uX, aU = uU;
+            double gS = dS;
 #pragma unroll
-                for (int q = 0; q < RPL; ++q) {
-                    const double s = sub_s[xc[q] | yc];
-                    const double lT = T[q], lY = Y[q], lU = U[q], lY2 = Y2[q], lS = S[q];
-                    const double nM = s + fmax(0.0, gS);
-                    const double nX = fmax(bd + aM, be + aX);
-                    const double nY = fmax(bd + lT, be + lY);   // bd + max(M, X) == max(bd + M, bd + X): rounding is monotone
-                    const double nY2 = fmax(lU, lY2);
-                    const double nU = fmax(nM, aU);
-                    const double nT = fmax(nM, nX);
-                    gS = lS;
-                    aM = nM; aX = nX; aU = nU;
-                    T[q] = nT; Y[q] = nY; U[q] = nU; Y2[q] = nY2; S[q] = fmax(nT, nY);
-                }
-                bM = aM; bX = aX;
-                dS = uS;
+            for (int q = 0; q < RPL; ++q) {
+                const double s = col[q * 5];
+                const double lT = T[q], lY = Y[q], lU = U[q], lY2 = Y2[q], lS = S[q];
+                const double nM = s + fmax(0.0, gS);
+                const double nX = fmax(bd + aM, be + aX);
+                const double nY = fmax(bd + lT, be + lY);   // bd + max(M, X) == max(bd + M, bd + X): rounding is monotone
+                const double nY2 = fmax(lU, lY2);
+                const double nU = fmax(nM, aU);
+                const double nT = fmax(nM, nX);
+                gS = lS;
+                aM = nM; aX = nX; aU = nU;
+                T[q] = nT; Y[q] = nY; U[q] = nU; Y2[q] = nY2; S[q] = fmax(nT, nY);
             }
-            if (t == L - 1 + last_lane && gl == last_lane) {
+            bM = aM; bX = aX;
+            dS = uS;
+            if (t - gl == L - 1) {
                 double u = U[0], y2 = Y2[0];
 #pragma unroll
                 for (int q = 1; q < RPL; ++q)
                     if (q == last_q) { u = U[q]; y2 = Y2[q]; }
-                result = p.inv_beta * fmax(0.0, fmax(u, y2));
+                best = fmax(0.0, fmax(u, y2));
             }
         }
+        if (gl == last_lane) result = p.inv_beta * best;
     }
     if (gl == last_lane && in_range && !skip) {
         p.out[r * p.ldo + c] = result;
@@ -240,7 +295,16 @@ int launch_la(const uint32_t* prow, const uint32_t* pcol, const LaParams& p, cud
     const int64_t pairs = p.rows * p.cols;
     const int64_t blocks = (pairs + GROUPS - 1) / GROUPS;
     KMG_REQUIRE(blocks < (1ll << 31), KMG_ERR_ARG, "local alignment: block too large for one launch");
-    la_kernel<LP, RPL><<<(unsigned)blocks, LA_THREADS, 0, stream>>>(prow, pcol, p);
+    constexpr int MINB = RPL <= 4 ? 5 : (RPL <= 8 ? 4 : 2);
+    constexpr size_t smem = (size_t)LA_THREADS * RPL * 5 * sizeof(double);
+    static bool attr_set[64] = {};
+    int dev = 0;
+    KMG_CUDA_CHECK(cudaGetDevice(&dev));
+    if (!attr_set[dev & 63]) {
+        KMG_CUDA_CHECK(cudaFuncSetAttribute(la_kernel<LP, RPL, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_set[dev & 63] = true;
+    }
+    la_kernel<LP, RPL, MINB><<<(unsigned)blocks, LA_THREADS, smem, stream>>>(prow, pcol, p);
     KMG_CUDA_CHECK(cudaGetLastError());
     return KMG_OK;
 }
@@ -255,9 +319,14 @@ int kmg_la_launch(const PairBlock* b, double e, double d, double beta, int smith
         KMG_REQUIRE(b->rows == b->cols && b->row_index0 == b->col_index0 && b->out_t != nullptr, KMG_ERR_ARG,
                     "symmetric mode needs a square diagonal block and a mirror destination");
     const int L = b->L;
-    // lanes per pair / rows per lane: two pairs per warp when 16 x 7 or 16 x 8 rows cover the sequence
-    const int lp = (L > 96) ? 16 : 32;
-    const int rpl = (L > 112) ? 8 : (L > 96 ? 7 : 4);
+    // lanes per pair / rows per lane.  The wavefront keeps LP lanes busy for L + LP - 1 steps of RPL cells: 10 201 of the
+    // 16 x 116 x 7 = 12 992 cell slots do work at L = 101 (78.5 %); four pairs per warp with 8 lanes x 13 rows fill
+    // 8 x 108 x 13 = 11 232 (90.8 %) at the price of 182 registers (8 warps per SM) -- still the faster one: 2048 x 4096 pairs
+    // in 81.0 ms against 84.1 ms (16 x 7) and 90.3 ms for the round-1 kernel on the same box.  KMG_LA_SHAPE=16 selects 16 x 7.
+    static const int shape = getenv("KMG_LA_SHAPE") ? atoi(getenv("KMG_LA_SHAPE")) : 8;
+    const bool wide = shape == 8 && L > 96 && L <= 104;
+    const int lp = wide ? 8 : ((L > 96) ? 16 : 32);
+    const int rpl = wide ? 13 : ((L > 112) ? 8 : (L > 96 ? 7 : 4));
     // worst-case growth of any state value per wavefront step, in bits: each of the RPL cells of a lane's column can
     // multiply by at most 3*max(e^{b s}) or e^{b d} + e^{b e}
     const double cell_bits = 1.4427 * beta * fmax(fmax(e, d), 9.0) + 2.0;
@@ -277,6 +346,7 @@ int kmg_la_launch(const PairBlock* b, double e, double d, double beta, int smith
     p.symmetric = b->symmetric;
     p.out = reinterpret_cast<double*>(b->out); p.ldo = b->ldo;
     p.out_t = reinterpret_cast<double*>(b->out_t); p.ldo_t = b->ldo_t;
+    if (lp == 8) return launch_la<8, 13>(b->planes_rows, b->planes_cols, p, stream);
     if (lp == 16 && rpl == 7) return launch_la<16, 7>(b->planes_rows, b->planes_cols, p, stream);
     if (lp == 16 && rpl == 8) return launch_la<16, 8>(b->planes_rows, b->planes_cols, p, stream);
     return launch_la<32, 4>(b->planes_rows, b->planes_cols, p, stream);

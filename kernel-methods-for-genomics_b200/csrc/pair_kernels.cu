@@ -24,6 +24,7 @@
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "gram_i8.h"
@@ -99,13 +100,14 @@ __device__ __forceinline__ double finish_f64(const OutSpec& o, int64_t r, int64_
 }
 
 // returns the fp64 value stored (0 for the s32 output, which takes no fused steps)
+template <bool EPI>
 __device__ __forceinline__ double store_int(const OutSpec& o, int64_t r, int64_t c, int64_t raw, bool mirror) {
     if (o.dtype == KMG_OUT_S32) {
         reinterpret_cast<int32_t*>(o.out)[r * o.ldo + c] = (int32_t)raw;
         if (mirror) reinterpret_cast<int32_t*>(o.out_t)[c * o.ldo_t + r] = (int32_t)raw;
         return 0.0;
     }
-    const double v = apply_epi(o, r, c, finish_int(o, r, c, raw));
+    const double v = EPI ? apply_epi(o, r, c, finish_int(o, r, c, raw)) : finish_int(o, r, c, raw);
     reinterpret_cast<double*>(o.out)[r * o.ldo + c] = v;
     if (mirror) reinterpret_cast<double*>(o.out_t)[c * o.ldo_t + r] = v;
     return v;
@@ -279,7 +281,9 @@ __device__ __forceinline__ void build_vmask(uint32_t (*vmask)[4], int L, int k) 
     }
 }
 
-template <int K, int B, int NW>
+// EPI: the fused ALIGNF / NLCK steps (epi_ops.cuh) are compiled into a separate instantiation: carrying them as dead code
+// costs the plain weighted-degree kernel 12 % (measured, same box), so the plain kernels carry none of it.
+template <int K, int B, int NW, bool EPI>
 __global__ void __launch_bounds__(TILE_R * TILE_C)
 mismatch_kernel(const uint32_t* __restrict__ prow, const uint32_t* __restrict__ pcol, const OutSpec o,
                 const MismatchParams mp) {
@@ -294,9 +298,13 @@ mismatch_kernel(const uint32_t* __restrict__ prow, const uint32_t* __restrict__ 
     const SeqPlanes x = kmg_load_planes(prow, live ? r : 0);
     const SeqPlanes y = kmg_load_planes(pcol, live ? c : 0);
     const int64_t raw = mismatch_pair<K, B, NW>(x, y, mp, vmask);
+    if (!EPI) {
+        if (live) store_int<false>(o, r, c, raw, cls == 1);
+        return;
+    }
     double v = 0.0;
-    if (live) v = store_int(o, r, c, raw, cls == 1);
-    if (o.epi && r < o.rows) epi_row_partial_warp(o.e, r, c0, v, live, threadIdx.x & 31);  // warp-uniform: r, c0
+    if (live) v = store_int<true>(o, r, c, raw, cls == 1);
+    if (r < o.rows) epi_row_partial_warp(o.e, r, c0, v, live, threadIdx.x & 31);  // warp-uniform: r, c0
 }
 
 template <int K, int B, int NW>
@@ -328,9 +336,14 @@ struct WdParams {
 constexpr int WD_PPT = 4;
 constexpr int WD_TILE_C = TILE_C * WD_PPT;
 
+
 // One k of the weighted-degree sum for the WD_PPT pairs of a thread: m &= (match >> (k-1)), c_k = popc(m),
 // acc += beta_k * c_k (kernels.py:74-80).  NW = words of the 128-bit vectors that can still be non-zero.
 // Returns true when no pair of the warp has a run of length k left (the remaining terms add +0.0).
+// Measured alternatives, same box, d = 10, 32768^2 (tools/ab_pair.sh): this form 1.285e11 entries/s; the run vector as its
+// own shifted operand (m_k = m_{k-1} & (m_{k-1} >> 1): no second array, 16 registers less, but shift and AND become one
+// serial chain) 1.135e11; voting on the population counts instead of OR-ing the run-vector words 1.19e11, the same
+// software-pipelined on the previous step's counts 1.11e11; retiring the four 32-pair slices one by one 1.09e11.
 template <int NW>
 __device__ __forceinline__ bool wd_step(uint32_t (&m)[WD_PPT][4], uint32_t (&sh)[WD_PPT][4], double (&acc)[WD_PPT], int k, double bk) {
     uint32_t any = 0u;
@@ -350,7 +363,7 @@ __device__ __forceinline__ bool wd_step(uint32_t (&m)[WD_PPT][4], uint32_t (&sh)
     if (__all_sync(0xffffffffu, any == 0u)) return true;
 #pragma unroll
     for (int j = 0; j < WD_PPT; ++j) {
-        // The XU pipe (POPC, I2F) is the busiest one (ncu 65 %): a carry-save adder over three of the four words
+        // The XU pipe (POPC, I2F) is the busiest one after the ALU: a carry-save adder over three of the four words
         // trades one POPC for two LOP3, and the exact int -> double conversion is one FP64 add of 2^52.
         const uint32_t s3 = m[j][0] ^ m[j][1] ^ m[j][2];
         const uint32_t cy = (m[j][0] & m[j][1]) | (m[j][2] & (m[j][0] ^ m[j][1]));
@@ -362,6 +375,7 @@ __device__ __forceinline__ bool wd_step(uint32_t (&m)[WD_PPT][4], uint32_t (&sh)
     return false;
 }
 
+template <bool EPI>
 __global__ void __launch_bounds__(TILE_R * TILE_C)
 wd_kernel(const uint32_t* __restrict__ prow, const uint32_t* __restrict__ pcol, const OutSpec o, const WdParams wp) {
     __shared__ double tile[TILE_R][WD_TILE_C + 1];
@@ -392,8 +406,7 @@ wd_kernel(const uint32_t* __restrict__ prow, const uint32_t* __restrict__ pcol, 
 #pragma unroll
     for (int j = 0; j < WD_PPT; ++j) acc[j] = 0.0;
     // The shifted match vector of iteration k is match >> (k-1), bits <= L - k: after the iteration k = L - 95 its fourth
-    // word is empty (and so is the run vector's), so the later iterations work on three words (L = 101: k >= 7, a
-    // quarter of the shift / and / popc work of those iterations).
+    // word is empty (and so is the run vector's), so the later iterations work on three words (L = 101: k >= 7, a quarter of the shift / and / popc work of those iterations).
     const int k4 = min(wp.d, wp.L - 95);  // last k done on all four words (<= 0: none)
     bool done = false;
 #pragma unroll 1
@@ -411,10 +424,10 @@ wd_kernel(const uint32_t* __restrict__ prow, const uint32_t* __restrict__ pcol, 
         const int64_t c = c0 + tc + 32 * j;
         const bool live = row_ok && c < o.cols;
         if (o.row_index0 + r == o.col_index0 + c) acc[j] = wp.diag;
-        if (live && (o.sd_rows != nullptr || o.epi)) acc[j] = apply_epi(o, r, c, finish_f64(o, r, c, acc[j]));
+        if (EPI && live) acc[j] = apply_epi(o, r, c, finish_f64(o, r, c, acc[j]));
         if (live) reinterpret_cast<double*>(o.out)[r * o.ldo + c] = acc[j];
         if (cls == 1) tile[tr][tc + 32 * j] = acc[j];
-        if (o.epi && row_ok && c0 + 32 * j < o.cols) epi_row_partial_warp(o.e, r, c0 + 32 * j, acc[j], live, tc);  // warp-uniform test
+        if (EPI && o.epi && row_ok && c0 + 32 * j < o.cols) epi_row_partial_warp(o.e, r, c0 + 32 * j, acc[j], live, tc);  // warp-uniform test
     }
     if (cls == 1) {  // mirror through shared memory so each column receives 8 consecutive doubles
         __syncthreads();
@@ -441,7 +454,7 @@ struct WdsParams {
     double delta[8];
 };
 
-template <int SMAX>
+template <int SMAX, bool EPI>
 __global__ void __launch_bounds__(TILE_R * TILE_C)
 wds_kernel(const uint32_t* __restrict__ prow, const uint32_t* __restrict__ pcol, const OutSpec o, const WdsParams wp) {
     __shared__ double tile[TILE_R][TILE_C + 1];
@@ -504,9 +517,9 @@ wds_kernel(const uint32_t* __restrict__ prow, const uint32_t* __restrict__ pcol,
         }
         c_t = __dadd_rn(c_t, __dmul_rn(wp.beta[k - 1], c_st));
     }
-    if (live && (o.sd_rows != nullptr || o.epi)) c_t = apply_epi(o, r, c, finish_f64(o, r, c, c_t));
+    if (EPI && live) c_t = apply_epi(o, r, c, finish_f64(o, r, c, c_t));
     if (live) reinterpret_cast<double*>(o.out)[r * o.ldo + c] = c_t;
-    if (o.epi && r < o.rows) epi_row_partial_warp(o.e, r, c0, c_t, live, tc);
+    if (EPI && o.epi && r < o.rows) epi_row_partial_warp(o.e, r, c0, c_t, live, tc);
     if (cls == 1) {
         tile[tr][tc] = c_t;
         __syncthreads();
@@ -541,13 +554,18 @@ template <int B, int NW>
 int launch_mismatch_k(const PairBlock* b, const OutSpec& o, const MismatchParams& mp, cudaStream_t stream) {
     dim3 grid((unsigned)((b->cols + TILE_C - 1) / TILE_C), (unsigned)((b->rows + TILE_R - 1) / TILE_R));
     dim3 block(TILE_R * TILE_C);
+    if (o.epi) {  // fused ALIGNF / NLCK steps: the runtime-k variant only (these calls are small)
+        mismatch_kernel<0, B, NW, true><<<grid, block, 0, stream>>>(b->planes_rows, b->planes_cols, o, mp);
+        KMG_CUDA_CHECK(cudaGetLastError());
+        return KMG_OK;
+    }
 #define KMG_MM_CASE(KK) \
-    case KK: mismatch_kernel<KK, B, NW><<<grid, block, 0, stream>>>(b->planes_rows, b->planes_cols, o, mp); break;
+    case KK: mismatch_kernel<KK, B, NW, false><<<grid, block, 0, stream>>>(b->planes_rows, b->planes_cols, o, mp); break;
     switch (mp.k) {
         KMG_MM_CASE(1) KMG_MM_CASE(2) KMG_MM_CASE(3) KMG_MM_CASE(4) KMG_MM_CASE(5) KMG_MM_CASE(6) KMG_MM_CASE(7)
         KMG_MM_CASE(8) KMG_MM_CASE(9) KMG_MM_CASE(10) KMG_MM_CASE(11) KMG_MM_CASE(12) KMG_MM_CASE(13) KMG_MM_CASE(14)
         KMG_MM_CASE(15) KMG_MM_CASE(16)
-        default: mismatch_kernel<0, B, NW><<<grid, block, 0, stream>>>(b->planes_rows, b->planes_cols, o, mp); break;
+        default: mismatch_kernel<0, B, NW, false><<<grid, block, 0, stream>>>(b->planes_rows, b->planes_cols, o, mp); break;
     }
 #undef KMG_MM_CASE
     KMG_CUDA_CHECK(cudaGetLastError());
@@ -670,7 +688,8 @@ int kmg_wd_launch(const PairBlock* b, int d, cudaStream_t stream) {
     for (int w = 0; w < 4; ++w) wp.posmask[w] = 0u;
     if (b->L >= 2) kmg_range_mask_128(1, b->L - 1, wp.posmask);
     dim3 grid((unsigned)((b->cols + WD_TILE_C - 1) / WD_TILE_C), (unsigned)((b->rows + TILE_R - 1) / TILE_R));
-    wd_kernel<<<grid, TILE_R * TILE_C, 0, stream>>>(b->planes_rows, b->planes_cols, o, wp);
+    if (o.epi || o.sd_rows != nullptr) wd_kernel<true><<<grid, TILE_R * TILE_C, 0, stream>>>(b->planes_rows, b->planes_cols, o, wp);
+    else wd_kernel<false><<<grid, TILE_R * TILE_C, 0, stream>>>(b->planes_rows, b->planes_cols, o, wp);
     KMG_CUDA_CHECK(cudaGetLastError());
     return KMG_OK;
 }
@@ -689,9 +708,14 @@ int kmg_wds_launch(const PairBlock* b, int d, int S, cudaStream_t stream) {
     for (int s = 0; s < 8; ++s) wp.delta[s] = 1.0 / 2.0 / (double)(s + 1);                        // kernels.py:112
     const OutSpec o = make_out(b);
     dim3 grid((unsigned)((b->cols + TILE_C - 1) / TILE_C), (unsigned)((b->rows + TILE_R - 1) / TILE_R));
-    if (S <= 1) wds_kernel<1><<<grid, TILE_R * TILE_C, 0, stream>>>(b->planes_rows, b->planes_cols, o, wp);
-    else if (S <= 3) wds_kernel<3><<<grid, TILE_R * TILE_C, 0, stream>>>(b->planes_rows, b->planes_cols, o, wp);
-    else wds_kernel<7><<<grid, TILE_R * TILE_C, 0, stream>>>(b->planes_rows, b->planes_cols, o, wp);
+    const bool epi = o.epi || o.sd_rows != nullptr;
+    if (epi) {
+        if (S <= 1) wds_kernel<1, true><<<grid, TILE_R * TILE_C, 0, stream>>>(b->planes_rows, b->planes_cols, o, wp);
+        else if (S <= 3) wds_kernel<3, true><<<grid, TILE_R * TILE_C, 0, stream>>>(b->planes_rows, b->planes_cols, o, wp);
+        else wds_kernel<7, true><<<grid, TILE_R * TILE_C, 0, stream>>>(b->planes_rows, b->planes_cols, o, wp);
+    } else if (S <= 1) wds_kernel<1, false><<<grid, TILE_R * TILE_C, 0, stream>>>(b->planes_rows, b->planes_cols, o, wp);
+    else if (S <= 3) wds_kernel<3, false><<<grid, TILE_R * TILE_C, 0, stream>>>(b->planes_rows, b->planes_cols, o, wp);
+    else wds_kernel<7, false><<<grid, TILE_R * TILE_C, 0, stream>>>(b->planes_rows, b->planes_cols, o, wp);
     KMG_CUDA_CHECK(cudaGetLastError());
     return KMG_OK;
 }

@@ -41,6 +41,8 @@ PROTOTYPES = {
     "kmg_dev_download": (_i32, [_vp, _vp, _i64]),
     "kmg_host_alloc": (_i32, [_i64, _vp]),
     "kmg_host_free": (_i32, [_vp]),
+    "kmg_set_d2h_mode": (_i32, [_i32]),
+    "kmg_get_d2h_mode": (_i32, []),
     "kmg_spectrum_host": (_i32, [_vp, _i64, _vp, _i64, _i32, _i32, _vp, _i32, _vp, _i64]),
     "kmg_mismatch_host": (_i32, [_vp, _i64, _vp, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _i64]),
     "kmg_spectrum_phi_host": (_i32, [_vp, _i64, _i32, _i32, _vp, _i32, _vp, _i64]),

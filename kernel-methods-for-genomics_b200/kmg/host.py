@@ -72,6 +72,54 @@ class _HostBlock:
 
 _POOL_MIN_BYTES = 1 << 22
 
+# ---- how fp64 results reach the host array (include/kmg.h KMG_D2H_*) -------------------------------------------------
+_MODES = {"widen": 0, "dma": 1, "mapped": 2}
+_AUTO_MIN_BYTES = 1 << 29  # results below 512 MB are not worth tuning for
+_auto = {"on": False, "rates": {}, "fixed": None}
+
+
+def set_d2h_mode(mode):
+    """"widen" (narrow integer transport + copy threads that widen to fp64), "dma" (fp64 straight into the pinned result
+    block by the copy engine), "mapped" (the kernel stores through the mapped address) or "auto": the first large results
+    of the process are delivered once in each of widen / dma, timed, and the faster mode is kept -- one process with many
+    cores is faster with widen, many processes sharing a host's cores with dma."""
+    if mode == "auto":
+        _auto.update(on=True, rates={}, fixed=None)
+        return
+    _auto["on"] = False
+    check(_cabi.lib().kmg_set_d2h_mode(_MODES[mode]))
+
+
+def get_d2h_mode():
+    return {v: k for k, v in _MODES.items()}[_cabi.lib().kmg_get_d2h_mode()]
+
+
+def _delivered(call, nbytes):
+    """Run `call` (one host builder); in auto mode time the large ones to choose the delivery mode."""
+    if not _auto["on"] or _auto["fixed"] is not None or nbytes < _AUTO_MIN_BYTES:
+        return call()
+    import time
+    mode = "widen" if "widen" not in _auto["rates"] else "dma"
+    check(_cabi.lib().kmg_set_d2h_mode(_MODES[mode]))
+    t0 = time.perf_counter()
+    out = call()
+    rate = nbytes / (time.perf_counter() - t0)
+    # the first call in a mode pays for cold pages / pinning: keep the best of two
+    prev = _auto["rates"].get(mode, (0.0, 0))
+    _auto["rates"][mode] = (max(prev[0], rate), prev[1] + 1)
+    if all(_auto["rates"].get(m, (0, 0))[1] >= 2 for m in ("widen", "dma")):
+        best = max(("widen", "dma"), key=lambda m: _auto["rates"][m][0])
+        _auto["fixed"] = best
+        check(_cabi.lib().kmg_set_d2h_mode(_MODES[best]))
+    elif _auto["rates"][mode][1] >= 2 and mode == "widen":
+        pass  # next call measures dma
+    return out
+
+
+import os as _os
+if _os.environ.get("KMG_D2H_MODE", "") == "auto":
+    _auto["on"] = True
+
 
 def _result(shape):
     """The float64 array a builder returns (the reference's np.zeros((n, n)), kernels.py:37).  Every entry point
@@ -87,8 +135,8 @@ def spectrum_gram(rows, ks, cols=None):
     rbuf, cbuf, fmt, nr, nc = _pair(rows, cols)
     K = _result((nr, nc))
     L = rbuf.shape[1] if nr else 1
-    check(_cabi.lib().kmg_spectrum_host(_ptr(rbuf), nr, _ptr(cbuf), 0 if cbuf is None else nc, L, fmt,
-                                        _ptr(ks), ks.size, _ptr(K), max(nc, 1)))
+    _delivered(lambda: check(_cabi.lib().kmg_spectrum_host(_ptr(rbuf), nr, _ptr(cbuf), 0 if cbuf is None else nc, L, fmt,
+                                                           _ptr(ks), ks.size, _ptr(K), max(nc, 1))), K.nbytes)
     return K
 
 
