@@ -244,6 +244,20 @@ int kmg_combine_dev(const double* const* d_Ks /* host array of device pointers *
 int kmg_weighted_dot_dev(const double* d_A, int64_t lda, const double* d_B, int64_t ldb, const double* d_w, int64_t n,
                          double* d_partial /* n */, double* d_result /* 1 */, void* stream);
 
+/* ---- closed-form solvers on resident Grams ------------------------------- */
+/* out = K v (rows x cols, row stride ld): KLR.IRLS's m = K alpha (KLR.py:37) */
+int kmg_matvec_dev(const double* d_K, int64_t rows, int64_t cols, int64_t ld, const double* d_v, double* d_out, void* stream);
+/* x = inv(S K S + c I) b with S = diag(d_s) (NULL: identity), blocked Cholesky in fp64 on the device.
+ *   KRR.fit  (KRR.py:33):   a = inv(K_fit + lambda n I) y              -> s = NULL, c = lambda n, b = y
+ *   KLR.WKRR (KLR.py:41-57): alpha = W^1/2 inv(W^1/2 K W^1/2 + n lambda I) W^1/2 z -> s = sqrt(W), c = n lambda, b = s * z, alpha = s * x
+ * d_work: kmg_spd_solve_workspace_bytes(n) bytes.  Synchronises the stream; KMG_ERR_ARG when the matrix is not positive definite. */
+int64_t kmg_spd_solve_workspace_bytes(int64_t n);
+int kmg_spd_solve_dev(const double* d_K, int64_t n, int64_t ld, const double* d_s, double c, const double* d_b, double* d_x, void* d_work,
+                      void* stream);
+/* the same from a host Gram: K_fit = K[idx][:, idx] (idx NULL: all of K, nfit = n) is gathered on the host and uploaded */
+int kmg_spd_solve_host(const double* K, int64_t n, int64_t ldk, const int64_t* idx, int64_t nfit, const double* s, double c,
+                       const double* b, double* x);
+
 /* (k,m)-mismatch common-neighbourhood table T[0..k] (host utility). */
 int kmg_mismatch_table_host(int k, int m, int64_t* T);
 

@@ -897,6 +897,58 @@ int kmg_combine_dev(const double* const* d_Ks, const int64_t* lds, const double*
     return kmg_ew_combine(d_Ks, lds, u, p, degree, rows, cols, d_out, ldo, (cudaStream_t)stream);
 }
 
+int kmg_matvec_dev(const double* d_K, int64_t rows, int64_t cols, int64_t ld, const double* d_v, double* d_out, void* stream) {
+    return kmg_ew_row_wsums(d_K, rows, cols, ld, d_v, d_out, (cudaStream_t)stream);
+}
+
+int64_t kmg_spd_solve_workspace_bytes(int64_t n) { return kmg_solve_workspace(n); }
+
+int kmg_spd_solve_dev(const double* d_K, int64_t n, int64_t ld, const double* d_s, double c, const double* d_b, double* d_x, void* d_work,
+                      void* stream) {
+    int rc = kmg_rt_require_device();
+    if (rc) return rc;
+    int* flag = nullptr;
+    if ((rc = kmg_spd_solve_launch(d_K, n, ld, d_s, c, d_b, d_x, d_work, &flag, (cudaStream_t)stream))) return rc;
+    int h = 0;
+    KMG_CUDA_CHECK(cudaMemcpyAsync(&h, flag, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    KMG_CUDA_CHECK(cudaStreamSynchronize((cudaStream_t)stream));
+    KMG_REQUIRE(h == 0, KMG_ERR_ARG, "spd_solve: the matrix S K S + c I is not positive definite");
+    return KMG_OK;
+}
+
+int kmg_spd_solve_host(const double* K, int64_t n, int64_t ldk, const int64_t* idx, int64_t nfit, const double* s, double c,
+                       const double* b, double* x) {
+    int rc = kmg_rt_require_device();
+    if (rc) return rc;
+    KMG_REQUIRE(K && b && x && n >= 0 && ldk >= n && (idx != nullptr || nfit == n) && nfit >= 0, KMG_ERR_ARG, "spd_solve: bad arguments");
+    if (nfit == 0) return KMG_OK;
+    for (int64_t t = 0; idx && t < nfit; ++t) KMG_REQUIRE(idx[t] >= 0 && idx[t] < n, KMG_ERR_ARG, "spd_solve: index out of range");
+    cudaStream_t st;
+    if ((rc = kmg_rt_get_streams(&st, nullptr))) return rc;
+    // K_fit = K[idx][:, idx] (KRR.py:30, KLR.py:67) gathered on the host: nfit^2 doubles cross PCIe, not n^2
+    std::vector<double> sub((size_t)nfit * nfit);
+    for (int64_t a = 0; a < nfit; ++a) {
+        const double* row = K + (idx ? idx[a] : a) * ldk;
+        for (int64_t q = 0; q < nfit; ++q) sub[a * nfit + q] = row[idx ? idx[q] : q];
+    }
+    DevBuf dK, ds, db, dx, work;
+    if ((rc = dK.alloc((size_t)nfit * nfit * 8))) return rc;
+    if ((rc = db.alloc((size_t)nfit * 8))) return rc;
+    if ((rc = dx.alloc((size_t)nfit * 8))) return rc;
+    if ((rc = work.alloc((size_t)kmg_solve_workspace(nfit)))) return rc;
+    KMG_CUDA_CHECK(cudaMemcpyAsync(dK.p, sub.data(), sub.size() * 8, cudaMemcpyHostToDevice, st));
+    KMG_CUDA_CHECK(cudaMemcpyAsync(db.p, b, (size_t)nfit * 8, cudaMemcpyHostToDevice, st));
+    if (s) {
+        if ((rc = ds.alloc((size_t)nfit * 8))) return rc;
+        KMG_CUDA_CHECK(cudaMemcpyAsync(ds.p, s, (size_t)nfit * 8, cudaMemcpyHostToDevice, st));
+    }
+    rc = kmg_spd_solve_dev(dK.as<double>(), nfit, nfit, s ? ds.as<double>() : nullptr, c, db.as<double>(), dx.as<double>(), work.p, st);
+    if (rc) { cudaStreamSynchronize(st); return rc; }
+    KMG_CUDA_CHECK(cudaMemcpyAsync(x, dx.p, (size_t)nfit * 8, cudaMemcpyDeviceToHost, st));
+    KMG_CUDA_CHECK(cudaStreamSynchronize(st));
+    return KMG_OK;
+}
+
 int kmg_weighted_dot_dev(const double* d_A, int64_t lda, const double* d_B, int64_t ldb, const double* d_w, int64_t n,
                          double* d_partial, double* d_result, void* stream) {
     return kmg_ew_weighted_dot(d_A, lda, d_B, ldb, d_w, n, d_partial, d_result, (cudaStream_t)stream);

@@ -36,3 +36,7 @@ int kmg_ew_row_wsums(const double* K, int64_t rows, int64_t cols, int64_t ld, co
 int kmg_ew_gather_vec(const double* v, const int64_t* idx, int64_t m, double* out, cudaStream_t s);
 // out = [out +] u * normalised(K), power / normalisation of the last term: the stored-Gram form of the fused accumulate epilogue
 int kmg_ew_accumulate(const double* K, int64_t ldk, const double* sd, const EpiOps* e, int64_t n, double* out, int64_t ldo, cudaStream_t s);
+// solve.cu: (S K S + c I) x = b on a device-resident symmetric K (KRR.py:33, KLR.py:41-57); work: kmg_solve_workspace(n) bytes
+int64_t kmg_solve_workspace(int64_t n);
+int kmg_spd_solve_launch(const double* K, int64_t n, int64_t ld, const double* s, double c, const double* b, double* x, void* work,
+                         int** d_flag, cudaStream_t st);

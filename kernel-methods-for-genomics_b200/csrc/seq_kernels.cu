@@ -86,8 +86,12 @@ spectrum_phi_kernel(const uint32_t* __restrict__ planes, int64_t n, int L, PhiPa
     extern __shared__ uint32_t row32[];  // Dpad bytes
     __shared__ uint8_t codes[KMG_MAX_L];
     const int64_t words = Dpad / 4;
+    // The row image is zeroed ONCE; after a row has been written out, the (at most L per k) counters it touched are
+    // cleared again by the threads that incremented them: ~700 shared-memory words per sequence instead of a 21 888-byte
+    // sweep (k = 1..7), which was half of the kernel's shared-memory traffic.
+    for (int64_t w = threadIdx.x; w < words; w += blockDim.x) row32[w] = 0u;
+    __syncthreads();
     for (int64_t seq = blockIdx.x; seq < n; seq += gridDim.x) {
-        for (int64_t w = threadIdx.x; w < words; w += blockDim.x) row32[w] = 0u;
         if (threadIdx.x < KMG_MAX_L) {
             const int pos = threadIdx.x;
             const uint32_t lo = __ldg(planes + seq * KMG_SEQ_WORDS + (pos >> 5));
@@ -110,6 +114,16 @@ spectrum_phi_kernel(const uint32_t* __restrict__ planes, int64_t n, int L, PhiPa
         uint4* dst = reinterpret_cast<uint4*>(phi + seq * ld);
         const uint4* src = reinterpret_cast<const uint4*>(row32);
         for (int64_t w = threadIdx.x; w < Dpad / 16; w += blockDim.x) dst[w] = src[w];
+        __syncthreads();
+        for (int q = 0; q < pp.nk; ++q) {  // un-count: the same windows, the same words
+            const int k = pp.ks[q];
+            const int p = threadIdx.x;
+            if (p + k <= L) {
+                uint32_t idx = 0;
+                for (int t = 0; t < k; ++t) idx = (idx << 2) | codes[p + t];
+                row32[(pp.off[q] + idx) >> 2] = 0u;
+            }
+        }
         __syncthreads();
     }
 }

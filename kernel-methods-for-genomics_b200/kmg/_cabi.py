@@ -88,6 +88,10 @@ PROTOTYPES = {
     "kmg_center_apply_dev": (_i32, [_vp, _i64, _i64, _i64, _i64, _vp, _vp, _vp, _vp, _i64, _vp]),
     "kmg_gather_dev": (_i32, [_vp, _i64, _vp, _i64, _vp, _i64, _vp]),
     "kmg_combine_dev": (_i32, [_vp, _vp, _vp, _i32, _i32, _i64, _i64, _vp, _i64, _vp]),
+    "kmg_matvec_dev": (_i32, [_vp, _i64, _i64, _i64, _vp, _vp, _vp]),
+    "kmg_spd_solve_workspace_bytes": (_i64, [_i64]),
+    "kmg_spd_solve_dev": (_i32, [_vp, _i64, _i64, _vp, _dbl, _vp, _vp, _vp, _vp]),
+    "kmg_spd_solve_host": (_i32, [_vp, _i64, _i64, _vp, _i64, _vp, _dbl, _vp, _vp]),
     "kmg_weighted_dot_dev": (_i32, [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _vp, _vp]),
     "kmg_mismatch_table_host": (_i32, [_i32, _i32, _vp]),
 }

@@ -278,6 +278,24 @@ def nlck_grad(kernels_fit, u, alpha, degree):
     return g
 
 
+def spd_solve(K, b, c, idx=None, s=None):
+    """x = inv(S K_fit S + c I) b with K_fit = K[idx][:, idx] (idx None: all of K), S = diag(s) (None: identity):
+    the K_fit algebra of KRR.fit (KRR.py:30-33) and KLR.WKRR (KLR.py:41-57) on the device (kmg_spd_solve_host)."""
+    K = np.ascontiguousarray(K, np.float64)
+    n = K.shape[0]
+    if idx is not None:
+        idx = np.ascontiguousarray(np.atleast_1d(idx), np.int64)
+    nfit = n if idx is None else idx.size
+    b = np.ascontiguousarray(b, np.float64)
+    if b.size != nfit:
+        raise ValueError("spd_solve: one right-hand-side entry per fit row")
+    if s is not None:
+        s = np.ascontiguousarray(s, np.float64)
+    x = np.zeros(nfit)
+    check(_cabi.lib().kmg_spd_solve_host(_ptr(K), n, K.shape[1], _ptr(idx), nfit, _ptr(s), float(c), _ptr(b), _ptr(x)))
+    return x
+
+
 def mismatch_table(k, m):
     T = np.zeros(k + 1, np.int64)
     check(_cabi.lib().kmg_mismatch_table_host(int(k), int(m), _ptr(T)))

@@ -66,6 +66,36 @@ class DeviceGram:
             _lib().kmg_dev_free(d_idx)
         return out
 
+    def matvec(self, v):
+        """K v on the device (KLR.IRLS's m = K alpha, KLR.py:37); v and the result are host vectors."""
+        v = np.ascontiguousarray(v, np.float64)
+        assert v.size == self.cols
+        dv, dout = DeviceGram(1, self.cols), DeviceGram(1, self.rows)
+        check(_lib().kmg_dev_upload(dv.ptr, v.ctypes.data_as(C.c_void_p), v.nbytes))
+        check(_lib().kmg_matvec_dev(self.ptr, self.rows, self.cols, self.cols, dv.ptr, dout.ptr, None))
+        return dout.to_host()[0]
+
+    def spd_solve(self, b, c, s=None):
+        """x = inv(S K S + c I) b with S = diag(s) (None: identity) by a blocked Cholesky on the device.
+        KRR.fit (KRR.py:33): spd_solve(y, lbda * n).  KLR.WKRR (KLR.py:41-57): sqrt(W) * spd_solve(sqrt(W) * z, n * lbda, s=sqrt(W))."""
+        n = self.rows
+        assert self.cols == n
+        b = np.ascontiguousarray(b, np.float64)
+        db, dx = DeviceGram(1, n), DeviceGram(1, n)
+        check(_lib().kmg_dev_upload(db.ptr, b.ctypes.data_as(C.c_void_p), b.nbytes))
+        ds = None
+        if s is not None:
+            s = np.ascontiguousarray(s, np.float64)
+            ds = DeviceGram(1, n)
+            check(_lib().kmg_dev_upload(ds.ptr, s.ctypes.data_as(C.c_void_p), s.nbytes))
+        work = C.c_void_p()
+        check(_lib().kmg_dev_malloc(int(_lib().kmg_spd_solve_workspace_bytes(n)), C.byref(work)))
+        try:
+            check(_lib().kmg_spd_solve_dev(self.ptr, n, self.cols, None if ds is None else ds.ptr, float(c), db.ptr, dx.ptr, work, None))
+        finally:
+            _lib().kmg_dev_free(work)
+        return dx.to_host()[0]
+
     def normalize_(self):
         """normalize_K (kernels.py:398-415) in place; returns True on the K[0,0]==1 early-out."""
         k00 = np.empty(1)
