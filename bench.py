@@ -518,6 +518,23 @@ def e2e_leg(torch, kh, codes, row0, R, n, world, args, barrier, allmax):
     del Kh
     if not ok:
         raise SystemExit("bench.py: the end-to-end result disagrees with the oracle")
+    # the same call with the copy engine writing fp64 straight into the (pinned) result array: what the host's memory system
+    # takes from the devices without any CPU in the data path (profiles/r2_host_dram_ceiling.txt)
+    try:
+        kh.set_d2h_mode("dma")
+        Kd = kh.spectrum_gram(rows_h, KS, cols=codes)
+        del Kd
+        barrier()
+        t0 = time.perf_counter()
+        Kd = kh.spectrum_gram(rows_h, KS, cols=codes)
+        dtd = allmax(time.perf_counter() - t0)
+        okd = bool(np.array_equal(Kd[100:116, 5000:5064], oc.spectrum_block(rows_h[100:116], codes[5000:5064], KS)))
+        del Kd
+        res["delivery"] = {"mode_timed": "widen (narrow transport + copy threads)", "dma_mode_value": e2e_rows * float(n) * world / dtd,
+                           "dma_mode_host_write_gbs": e2e_rows * float(n) * world * 8 / dtd / 1e9, "dma_mode_parity_checked": okd,
+                           "widen_mode_host_write_gbs": res["value"] * 8 / 1e9}
+    finally:
+        kh.set_d2h_mode("widen")
     return res
 
 

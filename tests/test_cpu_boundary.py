@@ -131,3 +131,44 @@ def test_select_method_parses_the_reference_dsl(monkeypatch, capsys):
     assert km.letter_to_num("ACGTN") == "1234N" and km.format("GATTACA").tolist() == [3, 1, 4, 4, 1, 2, 1]
     with pytest.raises(ValueError):
         km.format("ACGN")
+
+
+def test_fused_method_parser_follows_the_reference_dsl():
+    """kmg.fused.parse_method reads the reference's method strings with select_method's rule (kernels.py:479-502: the
+    first character of every '_' field is dropped; 'smith' / 'eig' words for LA); kernels outside the hot path raise."""
+    from kmg import fused
+    m = fused.parse_method("SP_k6")
+    assert (m.kind, m.k) == (fused.KIND_SP, 6)
+    m = fused.parse_method("MM_k10_m1")
+    assert (m.kind, m.k, m.m) == (fused.KIND_MM, 10, 1)
+    m = fused.parse_method("WD_d10")
+    assert (m.kind, m.d) == (fused.KIND_WD, 10)
+    m = fused.parse_method("WDS_d3_s2")
+    assert (m.kind, m.d, m.S) == (fused.KIND_WDS, 3, 2)
+    m = fused.parse_method("LA_e11_d1_b0.5_smith1_eig0")
+    assert (m.kind, m.e, m.dd, m.beta, m.smith) == (fused.KIND_LA, 11.0, 1.0, 0.5, 1)
+    for bad in ("SS_l1_k3", "GP_k3_g1", "XX_1"):
+        with pytest.raises(NotImplementedError):
+            fused.parse_method(bad)
+
+
+def test_solver_dropins_import_without_a_gpu():
+    """KRR.py / KLR.py / ALIGNF.py / NLCKernels.py mirror the reference's classes and import on a CPU-only box; the first
+    device call is what fails (no CPU fallback)."""
+    import numpy as np
+    import ALIGNF
+    import KLR
+    import KRR
+    import NLCKernels
+    from kmg import _cabi
+    assert hasattr(NLCKernels, "cross_validation") and hasattr(ALIGNF, "aligned_kernels")
+    assert hasattr(ALIGNF.ALIGNF, "from_sequences") and hasattr(NLCKernels.NLCK, "from_sequences")
+    m = KRR.KRR(np.eye(4), np.arange(4), lbda=0.5)
+    assert (m.lbda, m.eps) == (0.5, 1e-5)
+    k = KLR.KLR(np.eye(4), np.arange(4))
+    assert abs(k.sigmoid(0.0) - 0.5) < 1e-16
+    import pandas as pd
+    import torch
+    if not torch.cuda.is_available():
+        with pytest.raises(_cabi.KmgError):
+            m.fit(pd.DataFrame({"Id": [0, 1]}), pd.DataFrame({"Id": [0, 1], "Bound": [1.0, -1.0]}))
