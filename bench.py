@@ -284,12 +284,13 @@ def main():
 
     def build():
         if sym is not None:
-            issued[0] = float(sym.build_spectrum(phi[:R_tot]))
+            issued[0] = float(sym.build_spectrum(phi[:R_tot], defer_join=R_tot < n))
             launches[0] = sym.launches
-            if R_tot < n:
+            if R_tot < n:  # the plain remainder runs under the last peer copies of the shared square
                 kd.gram_i8(phi[row0:row0 + R], phi[R_tot:], row_index0=row0, col_index0=R_tot, out_dtype=1, m_sub=0, out=out[:, R_tot:])
                 issued[0] += float(R) * (n - R_tot)
                 launches[0] += 1
+                sym.join()
         elif sym1:
             kd.gram_i8(phi[:R], phi[:R], out_dtype=1, symmetric=True, m_sub=0, out=out[:, :R])
             issued[0], launches[0] = sym_issued_entries(R), 1
@@ -518,21 +519,32 @@ def e2e_leg(torch, kh, codes, row0, R, n, world, args, barrier, allmax):
     del Kh
     if not ok:
         raise SystemExit("bench.py: the end-to-end result disagrees with the oracle")
-    # the same call with the copy engine writing fp64 straight into the (pinned) result array: what the host's memory system
-    # takes from the devices without any CPU in the data path (profiles/r2_host_dram_ceiling.txt)
+    # The same call with the copy engine writing fp64 straight into the (pinned) result array -- no CPU in the data path.
+    # Which delivery is faster depends on how many processes share the host's cores and memory system (1 GPU: widen;
+    # profiles/r2_host_dram_ceiling.txt), so the library's "auto" setting times both on the first large results and keeps
+    # the faster; the value reported here is that steady state.
     try:
         kh.set_d2h_mode("dma")
-        Kd = kh.spectrum_gram(rows_h, KS, cols=codes)
-        del Kd
-        barrier()
-        t0 = time.perf_counter()
-        Kd = kh.spectrum_gram(rows_h, KS, cols=codes)
-        dtd = allmax(time.perf_counter() - t0)
+        Kd = kh.spectrum_gram(rows_h, KS, cols=codes)  # pins the result block
         okd = bool(np.array_equal(Kd[100:116, 5000:5064], oc.spectrum_block(rows_h[100:116], codes[5000:5064], KS)))
+        dtd = []
+        for _ in range(3):
+            del Kd
+            barrier()
+            t0 = time.perf_counter()
+            Kd = kh.spectrum_gram(rows_h, KS, cols=codes)
+            dtd.append(time.perf_counter() - t0)
         del Kd
-        res["delivery"] = {"mode_timed": "widen (narrow transport + copy threads)", "dma_mode_value": e2e_rows * float(n) * world / dtd,
-                           "dma_mode_host_write_gbs": e2e_rows * float(n) * world * 8 / dtd / 1e9, "dma_mode_parity_checked": okd,
-                           "widen_mode_host_write_gbs": res["value"] * 8 / 1e9}
+        dtd = allmax(float(np.mean(dtd)))
+        widen_value, dma_value = res["value"], e2e_rows * float(n) * world / dtd
+        res["delivery"] = {"widen_value": widen_value, "dma_value": dma_value, "dma_parity_checked": okd,
+                           "widen_host_write_gbs": widen_value * 8 / 1e9, "dma_host_write_gbs": dma_value * 8 / 1e9,
+                           "chosen": "dma" if (dma_value > widen_value and okd) else "widen",
+                           "what": "widen = u16/s32 over PCIe + copy threads widening to fp64; dma = fp64 by the copy engine into the pinned result array; "
+                                   "kmg.host.set_d2h_mode('auto') keeps the faster of the two"}
+        if res["delivery"]["chosen"] == "dma":
+            res["value"] = dma_value
+            res["d2h_bytes_per_step"] = int(e2e_rows * n * 8)
     finally:
         kh.set_d2h_mode("widen")
     return res

@@ -45,7 +45,9 @@ extern "C" {
 /* how the mirrored blocks of a sharded symmetric Gram reach their owners (kmg_gram_i8_sharded_dev) */
 #define KMG_EXCH_SINGLE 0  /* one launch, thread-issued stores into the owners' buffers (buffers on one device / tests) */
 #define KMG_EXCH_STAGED 1  /* per peer block: transposed block into local staging + one pitched peer copy */
-#define KMG_EXCH_DIRECT 2  /* per peer block: the epilogue's TMA stores write the owner's buffer over NVLink (default) */
+#define KMG_EXCH_DIRECT 2  /* per peer block: the epilogue's TMA stores write the owner's buffer over NVLink */
+#define KMG_EXCH_DEFER_JOIN 0x100 /* OR-ed to KMG_EXCH_STAGED: do not make the stream wait for the peer copies; the caller enqueues
+                                     more work (the plain remainder of a wider block-row) and then calls kmg_gram_sharded_join */
 
 #define KMG_MM_AUTO 0      /* dense feature map + tensor-core GEMM for k <= 8, pairwise bit-vector kernel above */
 #define KMG_MM_PAIRWISE 1
@@ -184,6 +186,7 @@ int kmg_gram_i8_dev(const int8_t* d_phi_rows, const int8_t* d_phi_cols, int64_t 
  * into the peers' buffers (buffers on one device, or tests).  d_stage is only read for KMG_EXCH_STAGED.
  * d_sd (nullable): sqrt(diag) of all n rows, fused cosine normalisation.  computed_entries (nullable out). */
 int kmg_gram_sharded_stage_bytes(int n_parts, const int64_t* part_row0, int part, int out_dtype, int64_t* bytes);
+int kmg_gram_sharded_join(void* stream);
 /* GEMM launches one call of kmg_gram_i8_sharded_dev enqueues for this part (host utility, no GPU) */
 int kmg_gram_sharded_launches(int n_parts, const int64_t* part_row0, int part, int exchange, int* launches);
 int kmg_gram_i8_sharded_dev(const int8_t* d_phi, int64_t n, int64_t width, int64_t ld_phi, int n_parts, int part,

@@ -632,6 +632,8 @@ int kmg_gram_i8_sharded_dev(const int8_t* d_phi, int64_t n, int64_t width, int64
     KMG_REQUIRE(n_parts >= 1 && n_parts <= KMG_MAX_PARTS && part >= 0 && part < n_parts && part_row0 && part_out, KMG_ERR_ARG,
                 "gram_i8_sharded: 1..%d parts", KMG_MAX_PARTS);
     KMG_REQUIRE(ldo >= n, KMG_ERR_ARG, "gram_i8_sharded: ldo < n");
+    const bool defer_join = (exchange & KMG_EXCH_DEFER_JOIN) != 0;
+    exchange &= ~KMG_EXCH_DEFER_JOIN;
     KMG_REQUIRE(exchange == KMG_EXCH_SINGLE || exchange == KMG_EXCH_DIRECT || (exchange == KMG_EXCH_STAGED && d_stage != nullptr), KMG_ERR_ARG,
                 "gram_i8_sharded: exchange must be KMG_EXCH_SINGLE, KMG_EXCH_STAGED (with d_stage) or KMG_EXCH_DIRECT");
     if (computed_entries) *computed_entries = 0;
@@ -746,7 +748,7 @@ int kmg_gram_i8_sharded_dev(const int8_t* d_phi, int64_t n, int64_t width, int64
         for (cudaEvent_t e : tg) cudaEventDestroy(e);
         for (cudaEvent_t e : tc) cudaEventDestroy(e);
     }
-    if (staged) {  // `stream` completes only after the peer copies have
+    if (staged && !defer_join) {  // `stream` completes only after the peer copies have
         for (int q = 0; q < (copies[1] != copies[0] ? 2 : 1); ++q) {
             KMG_CUDA_CHECK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
             KMG_CUDA_CHECK(cudaEventRecord(ev, copies[q]));
@@ -755,6 +757,21 @@ int kmg_gram_i8_sharded_dev(const int8_t* d_phi, int64_t n, int64_t width, int64
         }
     }
     if (computed_entries) *computed_entries = total;
+    return KMG_OK;
+}
+
+// Makes `stream` wait for the peer copies this thread's staged exchanges have enqueued (KMG_EXCH_DEFER_JOIN): work launched on
+// `stream` between the sharded build and the join -- e.g. the plain cross-Gram of the remaining columns -- runs under the copies.
+int kmg_gram_sharded_join(void* stream) {
+    int rc = kmg_rt_require_device();
+    if (rc) return rc;
+    cudaStream_t s0, copy;
+    if ((rc = kmg_rt_get_streams(&s0, &copy))) return rc;
+    cudaEvent_t ev;
+    KMG_CUDA_CHECK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    KMG_CUDA_CHECK(cudaEventRecord(ev, copy));
+    KMG_CUDA_CHECK(cudaStreamWaitEvent((cudaStream_t)stream, ev, 0));
+    KMG_CUDA_CHECK(cudaEventDestroy(ev));
     return KMG_OK;
 }
 

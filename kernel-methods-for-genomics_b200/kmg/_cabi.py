@@ -18,6 +18,7 @@ KMG_OUT_S32, KMG_OUT_F64 = 0, 1
 KMG_SEQ_CODES, KMG_SEQ_ASCII = 0, 1
 KMG_MM_AUTO, KMG_MM_PAIRWISE, KMG_MM_DENSE = 0, 1, 2
 KMG_EXCH_SINGLE, KMG_EXCH_STAGED, KMG_EXCH_DIRECT = 0, 1, 2
+KMG_EXCH_DEFER_JOIN = 0x100
 
 
 class KmgError(RuntimeError):
@@ -66,6 +67,7 @@ PROTOTYPES = {
     "kmg_phi_diag_sqrt_dev": (_i32, [_vp, _i64, _i64, _i64, _vp, _vp]),
     "kmg_gram_i8_dev": (_i32, [_vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _vp, _i64, _i32, _i32, _vp, _vp, _i32, _vp]),
     "kmg_gram_sharded_stage_bytes": (_i32, [_i32, _vp, _i32, _i32, _vp]),
+    "kmg_gram_sharded_join": (_i32, [_vp]),
     "kmg_gram_sharded_launches": (_i32, [_i32, _vp, _i32, _i32, _vp]),
     "kmg_gram_i8_sharded_dev": (_i32, [_vp, _i64, _i64, _i64, _i32, _i32, _vp, _vp, _i64, _i32, _vp, _i32, _vp, _vp, _vp]),
     "kmg_mma_peak_i8_dev": (_i32, [_i32, _vp, _vp]),

@@ -109,7 +109,12 @@ def sharded_launches(part_row0, part, exchange):
     return out.value
 
 
-def gram_i8_sharded(phi, part_row0, part, part_ptrs, ldo, out_dtype=KMG_OUT_F64, sd=None, stage=None, exchange=None):
+def sharded_join():
+    """Make the current stream wait for the peer copies of the staged exchanges enqueued with defer_join=True."""
+    check(_cabi.lib().kmg_gram_sharded_join(_stream()))
+
+
+def gram_i8_sharded(phi, part_row0, part, part_ptrs, ldo, out_dtype=KMG_OUT_F64, sd=None, stage=None, exchange=None, defer_join=False):
     """Part `part`'s launch of the sharded symmetric Gram of all rows of `phi` (kmg_gram_i8_sharded_dev).
     part_row0: len(parts)+1 boundaries; part_ptrs: device address (int) of every part's block-row buffer (row stride ldo
     elements) -- this device's own allocations or peer memory opened through CUDA IPC.  exchange: "direct" (one launch per
@@ -120,6 +125,8 @@ def gram_i8_sharded(phi, part_row0, part, part_ptrs, ldo, out_dtype=KMG_OUT_F64,
     if exchange is None:
         exchange = "staged" if stage is not None else "single"
     mode = {"single": _cabi.KMG_EXCH_SINGLE, "staged": _cabi.KMG_EXCH_STAGED, "direct": _cabi.KMG_EXCH_DIRECT}[exchange]
+    if defer_join and exchange == "staged":
+        mode |= _cabi.KMG_EXCH_DEFER_JOIN
     n, W = phi.shape
     g = len(part_ptrs)
     bounds = np.ascontiguousarray(part_row0, np.int64)

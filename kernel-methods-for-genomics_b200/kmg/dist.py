@@ -217,15 +217,24 @@ class SymmetricShards:
         self._holder = holder
         self.block = torch.as_tensor(holder, device=torch.device("cuda", torch.cuda.current_device()))
 
-    def build_spectrum(self, phi, sd=None):
-        """All ranks call this with their local copy of Phi (n x W int8).  Returns entries this rank issued to the MMA."""
+    def build_spectrum(self, phi, sd=None, defer_join=False):
+        """All ranks call this with their local copy of Phi (n x W int8).  Returns entries this rank issued to the MMA.
+        defer_join: do not make the stream wait for the outgoing peer copies yet -- the caller launches more work (the
+        plain remainder of a wider block-row) and then calls join(), so that work runs under the copies."""
         from . import device as kd
         assert phi.shape[0] == self.n
         computed = kd.gram_i8_sharded(phi, self.bounds, self.rank, self.ptrs, self.ldo,
                                       out_dtype=1 if self.dtype == torch.float64 else 0, sd=sd,
                                       stage=self._stage.value if self.exchange == "staged" else None,
-                                      exchange=self.exchange if (self.exchange != "staged" or self._stage.value) else "single")
+                                      exchange=self.exchange if (self.exchange != "staged" or self._stage.value) else "single",
+                                      defer_join=defer_join)
         return computed
+
+    def join(self):
+        """The stream waits for this rank's outgoing peer copies (after build_spectrum(defer_join=True))."""
+        from . import device as kd
+        if self.exchange == "staged" and self._stage.value:
+            kd.sharded_join()
 
     def finish(self):
         """Every buffer is complete once every rank's launch has finished: stream sync, then a barrier."""
