@@ -372,7 +372,7 @@ def main():
         "cublaslt_int8_same_run": cublaslt,
         "algorithmic_ops_per_step": alg_ops, "kernel_ms": gemm_avg_ms, "kernel_ms_max_over_ranks": gemm_max_ms,
         "kernel_share_of_step": gemm_avg_ms / ms_per_step,
-        "traffic": TRAFFIC_BYTES_PER_LAUNCH if (sym is None and not sym1) else None,
+        "traffic": TRAFFIC_BYTES_N1_STEP if sym1 else (TRAFFIC_BYTES_PER_LAUNCH if sym is None else None),
         "traffic_source": TRAFFIC_SOURCE,
         "hbm_write_gbs": 8.0 * R * n / (gemm_avg_ms * 1e-3) / 1e9,
         "gemm_launches_per_step": launches[0], "entries_issued_over_entries_held": issued[0] / (float(R) * n),
@@ -426,9 +426,13 @@ def main():
 # ncu captures summarised in profiles/ (the reads are the operand panels streamed once per wave of 74 tiles; L2 eviction
 # hints and other band heights were measured in round 2 and change nothing: profiles/r2_gemm_l2_hints.txt)
 TRAFFIC_BYTES_PER_LAUNCH = 146_286_971_904
-TRAFFIC_SOURCE = ("ncu dram__bytes_read.sum 106.30 GB + dram__bytes_write.sum 39.99 GB, one plain 25000 x 200000 launch "
-                  "(profiles/r2_gemm_l2_hints.txt h0_b8, same kernel and shape as profiles/r1_gemm_ncu_full_summary.txt); "
-                  "null when the step is the symmetric build (several launches)")
+# the two launches of the N = 1 step (25 000^2 symmetric with TMA mirror stores + 25 000 x 175 000 plain):
+# 6.70 + 4.96 GB and 93.65 + 34.98 GB, profiles/r2_gemm_ncu_full_summary.txt
+TRAFFIC_BYTES_N1_STEP = 140_297_595_000
+TRAFFIC_SOURCE = ("ncu --set full dram__bytes_read.sum + dram__bytes_write.sum: N = 1 step (symmetric 25000^2 + plain 25000 x 175000 launch) "
+                  "100.35 + 39.95 GB, profiles/r2_gemm_ncu_full_summary.txt; one plain 25000 x 200000 launch (--no-sym) 106.30 + 39.99 GB, "
+                  "profiles/r2_gemm_l2_hints.txt; null for the sharded build at N > 1 (ncu cannot follow a torchrun job); algorithmic minimum "
+                  "40 GB written + 4.4 GB of Phi read once")
 
 
 def check_parity(torch, out, codes, row0, R, n, R_tot, rank, world):

@@ -22,6 +22,15 @@ if a.kind == "gemm":
     phi = kd.spectrum_phi(planes, 101, ks)
     out = torch.empty((a.rows, a.cols), dtype=torch.float64 if a.dt else torch.int32, device="cuda")
     fn = lambda: kd.gram_i8(phi[:a.rows], phi[:a.cols], out_dtype=a.dt, m_sub=a.m_sub, out=out)
+elif a.kind == "n1job":
+    # the N = 1 job of bench.py: 25 000^2 symmetric (in-place TMA mirror stores) + 25 000 x 175 000 plain
+    R, nn = 25000, 200000
+    planes = kd.pack(onp.synthetic_codes(nn, 101, seed=3), 0)
+    phi = kd.spectrum_phi(planes, 101, [1, 2, 3, 4, 5, 6, 7])
+    out = torch.empty((R, nn), dtype=torch.float64, device="cuda")
+    def fn():
+        kd.gram_i8(phi[:R], phi[:R], out_dtype=1, symmetric=True, out=out[:, :R])
+        kd.gram_i8(phi[:R], phi[R:], row_index0=0, col_index0=R, out_dtype=1, out=out[:, R:])
 elif a.kind == "wd":
     out = torch.empty((a.rows, a.cols), dtype=torch.float64, device="cuda")
     fn = lambda: kd.wd_block(planes[:a.rows], planes[:a.cols], 101, 10, out=out)
