@@ -295,16 +295,30 @@ int launch_la(const uint32_t* prow, const uint32_t* pcol, const LaParams& p, cud
     const int64_t pairs = p.rows * p.cols;
     const int64_t blocks = (pairs + GROUPS - 1) / GROUPS;
     KMG_REQUIRE(blocks < (1ll << 31), KMG_ERR_ARG, "local alignment: block too large for one launch");
-    constexpr int MINB = RPL <= 4 ? 5 : (RPL <= 8 ? 4 : 2);
+    // Resident blocks per SM: occupancy is what this kernel needs most (FP64 chains down a lane's rows; ncu: "wait" is the
+    // top stall).  8 x 13 strips: 3 blocks of 128 threads at 168 registers (44 bytes of spills) run 2048 x 4096 pairs in
+    // 68.8 ms against 81.0 ms with 2 blocks at 182 registers (4 blocks: 128 registers, 944 bytes of spills, 296 ms);
+    // 16 x 7 strips: 5 blocks at 96 registers (36 bytes of spills) 80.6 ms, 4 blocks at 120 registers 84.1 ms.
+    constexpr int MINB_DEFAULT = RPL <= 8 ? 5 : 3;
     constexpr size_t smem = (size_t)LA_THREADS * RPL * 5 * sizeof(double);
-    static bool attr_set[64] = {};
+    static const int minb_env = getenv("KMG_LA_MIN_BLOCKS") ? atoi(getenv("KMG_LA_MIN_BLOCKS")) : 0;
+    static bool attr_set[64][8] = {};
     int dev = 0;
     KMG_CUDA_CHECK(cudaGetDevice(&dev));
-    if (!attr_set[dev & 63]) {
-        KMG_CUDA_CHECK(cudaFuncSetAttribute(la_kernel<LP, RPL, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set[dev & 63] = true;
-    }
-    la_kernel<LP, RPL, MINB><<<(unsigned)blocks, LA_THREADS, smem, stream>>>(prow, pcol, p);
+#define KMG_LA_LAUNCH(MB)                                                                                                              \
+    do {                                                                                                                               \
+        if (!attr_set[dev & 63][MB]) {                                                                                                 \
+            KMG_CUDA_CHECK(cudaFuncSetAttribute(la_kernel<LP, RPL, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));    \
+            attr_set[dev & 63][MB] = true;                                                                                             \
+        }                                                                                                                              \
+        la_kernel<LP, RPL, MB><<<(unsigned)blocks, LA_THREADS, smem, stream>>>(prow, pcol, p);                                       \
+    } while (0)
+    const int minb = minb_env ? minb_env : MINB_DEFAULT;
+    if (minb <= 2) KMG_LA_LAUNCH(2);
+    else if (minb == 3) KMG_LA_LAUNCH(3);
+    else if (minb == 4) KMG_LA_LAUNCH(4);
+    else KMG_LA_LAUNCH(5);
+#undef KMG_LA_LAUNCH
     KMG_CUDA_CHECK(cudaGetLastError());
     return KMG_OK;
 }
@@ -321,8 +335,8 @@ int kmg_la_launch(const PairBlock* b, double e, double d, double beta, int smith
     const int L = b->L;
     // lanes per pair / rows per lane.  The wavefront keeps LP lanes busy for L + LP - 1 steps of RPL cells: 10 201 of the
     // 16 x 116 x 7 = 12 992 cell slots do work at L = 101 (78.5 %); four pairs per warp with 8 lanes x 13 rows fill
-    // 8 x 108 x 13 = 11 232 (90.8 %) at the price of 182 registers (8 warps per SM) -- still the faster one: 2048 x 4096 pairs
-    // in 81.0 ms against 84.1 ms (16 x 7) and 90.3 ms for the round-1 kernel on the same box.  KMG_LA_SHAPE=16 selects 16 x 7.
+    // 8 x 108 x 13 = 11 232 (90.8 %).  2048 x 4096 pairs, same box: 68.8 ms (8 x 13, 3 blocks per SM) against 84.1 ms (16 x 7) and
+    // 90.3 ms for the round-1 kernel.  KMG_LA_SHAPE=16 selects 16 x 7.
     static const int shape = getenv("KMG_LA_SHAPE") ? atoi(getenv("KMG_LA_SHAPE")) : 8;
     const bool wide = shape == 8 && L > 96 && L <= 104;
     const int lp = wide ? 8 : ((L > 96) ? 16 : 32);

@@ -150,4 +150,12 @@ def test_sharded_plan_matches_the_assignment_rule():
                         want += width[I] * width[J]
             got = C.c_int64(-1)
             _cabi.check(lib.kmg_gram_sharded_stage_bytes(world, bd.ctypes.data_as(C.c_void_p), a, 1, C.byref(got)))
-            assert want * 8 <= got.value <= want * 8 + 256 * 2 * world, (n, world, a, want * 8, got.value)  # <= 2 pieces per peer block, each padded to 256 B
+            assert want * 8 <= got.value <= want * 8 + 256 * 2 * world, (n, world, a, want * 8, got.value)
+            # launches of one call: 2 column pieces per full block (1 when a block is a single tile wide), the half
+            # block at distance world/2, the diagonal block; the single-launch exchange is one launch
+            launches = C.c_int(-1)
+            _cabi.check(lib.kmg_gram_sharded_launches(world, bd.ctypes.data_as(C.c_void_p), a, _cabi.KMG_EXCH_STAGED, C.byref(launches)))
+            full = sum(1 for d in range(1, world) if 2 * d < world)
+            assert 1 + full <= launches.value <= 1 + 2 * full + (1 if world % 2 == 0 else 0), (n, world, a, launches.value)
+            _cabi.check(lib.kmg_gram_sharded_launches(world, bd.ctypes.data_as(C.c_void_p), a, _cabi.KMG_EXCH_SINGLE, C.byref(launches)))
+            assert launches.value == 1  # <= 2 pieces per peer block, each padded to 256 B
