@@ -102,6 +102,19 @@ def wd_block_row(planes, L, d, n, group=None):
     return build_block_row(lambda r0, r1: kd.wd_block(planes[r0:r1], planes, L, d, row_index0=r0), n, group)
 
 
+def wds_block_row(planes, L, d, S, n, group=None):
+    from . import device as kd
+    return build_block_row(lambda r0, r1: kd.wds_block(planes[r0:r1], planes, L, d, S, row_index0=r0), n, group)
+
+
+def la_block_row(planes, L, e, d, beta, n, smith=0, group=None, align=8):
+    """This rank's block-row of the local-alignment Gram (BASELINE configs[4]).  K[i, j] is evaluated with x = the sequence
+    of smaller index (kernels.py:289-291), which the kernel derives from the global row / column indices, so block-rows
+    built on different ranks are the rows of the one symmetric matrix.  One warp handles four pairs: no tile alignment."""
+    from . import device as kd
+    return build_block_row(lambda r0, r1: kd.la_block(planes[r0:r1], planes, L, e, d, beta, smith, row_index0=r0), n, group, align)
+
+
 def mismatch_block_row(planes, L, k, m, n, normalize=True, group=None):
     from . import device as kd
     sd = kd.mismatch_diag_sqrt(planes, L, k, m) if normalize else None  # every rank computes all n diagonals: no collective

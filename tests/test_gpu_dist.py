@@ -37,6 +37,11 @@ def test_block_row_builders_single_process(torch_cuda, dna):
     _, _, blk = kdist.mismatch_block_row(planes[:200], 101, 10, 1, 200)
     want = onp.normalize_K(oc.mismatch_raw_block(c[:200], c[:200], 10, 1).astype(np.float64))
     assert np.array_equal(blk.cpu().numpy(), want)
+    _, _, blk = kdist.la_block_row(planes[:64], 101, -11, -1, 0.5, 64)
+    want = oc.la_block(c[:64], c[:64], -11, -1, 0.5, 0)
+    assert np.all(np.abs(blk.cpu().numpy() - want) <= 1e-12 * np.abs(want))
+    _, _, blk = kdist.wds_block_row(planes[:48], 101, 4, 2, 48)
+    assert np.array_equal(blk.cpu().numpy(), onp.wds_gram(c[:48], 4, 2))
     # sharded pieces against the fused single-device centring
     sub = kd.wd_block(planes[128:384], planes, 101, 7, row_index0=128)
     rs, cs = kd.row_sums(sub), kd.col_sums(sub)
@@ -87,6 +92,9 @@ def _nccl_worker(rank, world, port, q):
                 assert torch.equal(shards.block, single[shards.r0:shards.r1]), staged
                 assert computed < 0.75 * (shards.r1 - shards.r0) * n
             shards.close()
+        lr0, lr1, lblk = kdist.la_block_row(planes[:512], 101, 11, 1, 0.5, 512)   # rows of ONE symmetric matrix across ranks
+        lfull = kd.la_block(planes[:512], planes[:512], 101, 11, 1, 0.5, 0, symmetric=True)
+        assert torch.equal(lblk, lfull[lr0:lr1])
         _, _, wblk = kdist.wd_block_row(planes, 101, 10, n)
         wfull = kd.wd_block(planes, planes, 101, 10, symmetric=True)
         cen = kdist.center_block_row(wblk, n)                       # all-reduce of n+1 doubles
