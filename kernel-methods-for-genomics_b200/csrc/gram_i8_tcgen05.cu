@@ -67,6 +67,7 @@ struct KernelParams {
     const double* sd_cols;
     const int4* tiles;  // {row_tile, col_tile, mirror, destination part of the mirror store}
     uint32_t* wave_counter;  // grid-wide arrival counter (zeroed before the launch) or null
+    int32_t wave_wait_kb;    // K-slab of a tile before which the producer waits for the wave (0: at the tile start)
     uint64_t hint_a, hint_b;  // L2 eviction policy of the A / B operand loads
 };
 
@@ -556,19 +557,24 @@ gram_i8_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             for (int t = cluster_id; t < p.ntiles; t += num_clusters, ++wave) {
                 const int4 tile = p.tiles[t];
                 const int32_t row0 = tile.x * C::BM + (int)rank * 128, col0 = tile.y * BN + (int)rank * 128;
-                if (p.wave_counter != nullptr) {  // see gram_i8_tcgen05_kernel: all CTAs start their w-th tile together
-                    ptx::red_release_gpu_add(p.wave_counter, 1u);
-                    const uint32_t done = (wave + 1) * gridDim.x;
-                    const uint32_t target = done < 2u * (uint32_t)p.ntiles ? done : 2u * (uint32_t)p.ntiles;
-                    if (ptx::ld_acquire_gpu(p.wave_counter) < target) {
-                        const uint64_t t0 = ptx::globaltimer_ns();
-                        while (ptx::ld_acquire_gpu(p.wave_counter) < target) {
-                            __nanosleep(200);
-                            if (ptx::globaltimer_ns() - t0 > 4000000000ull) __trap();
+                // Wave barrier (see gram_i8_tcgen05_kernel): all CTAs work on their w-th tile together.  A CTA announces its
+                // arrival at the tile start but waits for the others only before its (STAGES+1)-th K-slab: the slabs that
+                // fit the operand pipeline are loaded right away, so the pipeline does not drain at every tile boundary
+                // while the slowest CTA of the wave finishes (the early slabs of a wave's panels stay in L2 for the
+                // microseconds the stragglers need).
+                if (p.wave_counter != nullptr) ptx::red_release_gpu_add(p.wave_counter, 1u);
+                for (int kb = 0; kb < p.kblocks; ++kb) {
+                    if (p.wave_counter != nullptr && kb == p.wave_wait_kb) {
+                        const uint32_t done = (wave + 1) * gridDim.x;
+                        const uint32_t target = done < 2u * (uint32_t)p.ntiles ? done : 2u * (uint32_t)p.ntiles;
+                        if (ptx::ld_acquire_gpu(p.wave_counter) < target) {
+                            const uint64_t t0 = ptx::globaltimer_ns();
+                            while (ptx::ld_acquire_gpu(p.wave_counter) < target) {
+                                __nanosleep(200);
+                                if (ptx::globaltimer_ns() - t0 > 4000000000ull) __trap();
+                            }
                         }
                     }
-                }
-                for (int kb = 0; kb < p.kblocks; ++kb) {
                     ptx::mbar_wait(&empty[stage], phase ^ 1);
                     if (rank == 0) ptx::mbar_arrive_expect_tx(&full[stage], 2 * C::STAGE_BYTES);
                     uint8_t* sa = smem + stage * C::STAGE_BYTES;
@@ -1039,6 +1045,9 @@ int kmg_gram_i8_launch(const GramI8Args* a, cudaStream_t stream) {
     p.sd_rows = a->sd_rows; p.sd_cols = a->sd_cols;
     p.tiles = tl.dev;
     p.wave_counter = nullptr;
+    static const int wave_wait_env = env_int("KMG_GEMM_WAVE_WAIT", -1);
+    const int wave_wait = wave_wait_env >= 0 ? wave_wait_env : (pair ? Cfg2::STAGES : 0);
+    p.wave_wait_kb = wave_wait < p.kblocks ? wave_wait : 0;
     // the wave barrier only pays when the operands do not stay in L2 on their own (126 MB, two partitions)
     // one wave touches ~27 operand panels of 256 rows x Dpad bytes: below ~8 KB of features per row they all sit in L2
     const bool spills_l2 = a->Dpad >= 8192 && (double)(a->rows + a->cols) * (double)a->Dpad > 96e6;
