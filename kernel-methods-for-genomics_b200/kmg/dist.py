@@ -249,6 +249,31 @@ class SymmetricShards:
         if self.exchange == "staged" and self._stage.value:
             kd.sharded_join()
 
+    def needed_row_ranges(self):
+        """Rows of Phi this rank's launches read: its own block and the column blocks at cyclic distance 1 .. world/2 (the
+        part of the block at distance world/2 it computes), merged into ascending (lo, hi) ranges.  The rows of the other
+        blocks only enter tiles that other ranks compute and deliver, so this rank need not build their features."""
+        g, a, b = self.world, self.rank, self.bounds
+        need = [(b[a], b[a + 1])]
+        for d in range(1, g):
+            if 2 * d > g:
+                break
+            p = (a + d) % g
+            lo, hi = b[p], b[p + 1]
+            if 2 * d == g and a > p:  # the higher-numbered part computes the columns from the split on
+                tiles = -(-(b[p + 1] - b[p]) // TILE_ALIGN)
+                lo = min(b[p] + (tiles + 1) // 2 * TILE_ALIGN, b[p + 1])
+            if hi > lo:
+                need.append((lo, hi))
+        need.sort()
+        merged = [list(need[0])]
+        for lo, hi in need[1:]:
+            if lo <= merged[-1][1]:
+                merged[-1][1] = max(merged[-1][1], hi)
+            else:
+                merged.append([lo, hi])
+        return [tuple(r) for r in merged]
+
     def finish(self):
         """Every buffer is complete once every rank's launch has finished: stream sync, then a barrier."""
         torch.cuda.synchronize()

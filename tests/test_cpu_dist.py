@@ -159,3 +159,33 @@ def test_sharded_plan_matches_the_assignment_rule():
             assert 1 + full <= launches.value <= 1 + 2 * full + (1 if world % 2 == 0 else 0), (n, world, a, launches.value)
             _cabi.check(lib.kmg_gram_sharded_launches(world, bd.ctypes.data_as(C.c_void_p), a, _cabi.KMG_EXCH_SINGLE, C.byref(launches)))
             assert launches.value == 1  # <= 2 pieces per peer block, each padded to 256 B
+
+
+def test_needed_phi_rows_cover_exactly_what_the_launches_read():
+    """SymmetricShards.needed_row_ranges (the Phi rows a rank builds in bench.py): every row or column tile of every tile the
+    assignment rule gives the rank lies inside the ranges, and the ranges hold at most one tile more than that."""
+    from kmg import dist as kdist
+
+    class Fake:
+        pass
+    for n, world in ((200000, 8), (100000, 4), (50000, 2), (9000, 3), (7000, 5), (4096, 1)):
+        bounds = kdist.sym_bounds(n, world)
+        tiles = -(-n // 256)
+        owner = [max(p for p in range(world) if bounds[p] <= 256 * t) for t in range(tiles)]
+        for a in range(world):
+            f = Fake()
+            f.world, f.rank, f.bounds = world, a, bounds
+            ranges = kdist.SymmetricShards.needed_row_ranges(f)
+            assert all(lo < hi for lo, hi in ranges) and all(r[1] < s[0] for r, s in zip(ranges, ranges[1:]))
+            need = np.zeros(tiles, bool)
+            for I in range(tiles):
+                if owner[I] != a:
+                    continue
+                for J in range(tiles):
+                    if kdist.sym_takes(bounds, a, owner[J], I, J):
+                        need[I] = need[J] = True
+            got = np.zeros(tiles, bool)
+            for lo, hi in ranges:
+                got[lo // 256: -(-hi // 256)] = True
+            assert np.all(got[need]), (n, world, a, ranges)
+            assert got.sum() - need.sum() <= 1, (n, world, a)
