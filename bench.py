@@ -214,6 +214,7 @@ def main():
     ap.add_argument("--rows", type=int, default=ROWS_PER_GPU, help="(debug) rows per GPU")
     ap.add_argument("--no-sym", action="store_true", help="plain block-rows: no symmetric sharing of the leading square")
     ap.add_argument("--exchange", default=None, help="N > 1: staged | direct | single (default: kmg/dist.py's, KMG_SYM_EXCHANGE)")
+    ap.add_argument("--single-buffer", action="store_true", help="N > 1: one set of block-row buffers (a step waits for its own peer copies)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -257,7 +258,7 @@ def main():
     W = kd.phi_width(KS)
     phi = torch.empty((n, W), dtype=torch.int8, device="cuda")
     R_tot = min(n, world * R)  # the job: rows [0, R_tot) of the Gram
-    sym, exchange = None, {"mode": "n/a (1 GPU: in-place mirror stores)"}
+    sym, sym_b, exchange = None, None, {"mode": "n/a (1 GPU: in-place mirror stores)"}
     if world > 1 and not args.no_sym:
         from kmg import dist as kdist
         try:
@@ -270,8 +271,24 @@ def main():
                 sym.close()
             sym, note = None, note if ok == 0 else "plain block-rows (another rank could not map peer memory)"
         exchange = {"mode": note}
+        # Two sets of block-row buffers (2 x 57 GB per GPU at N = 8): consecutive Grams are built into alternate sets, so a
+        # build does not wait for its own outgoing peer copies -- they drain under the next build -- and the build after
+        # that waits for exactly those copies (kmg_gram_sharded_mark / wait_mark) before it reuses the buffers.
+        if sym is not None and sym.exchange == "staged" and not args.single_buffer:
+            try:
+                sym_b = kdist.SymmetricShards(R_tot, ldo=n, exchange=args.exchange)
+                ok = 1
+            except Exception:  # noqa: BLE001 - not enough memory: single buffering
+                ok = 0
+            if allmin_int(ok) == 0:
+                if sym_b is not None:
+                    sym_b.close()
+                sym_b = None
+        exchange["buffers"] = 2 if sym_b is not None else 1
     elif world > 1:
         exchange = {"mode": "plain block-rows (--no-sym)"}
+    syms = [s for s in (sym, sym_b) if s is not None]
+    step_no = [0]
     if sym is not None:
         row0, R, out = sym.r0, sym.r1 - sym.r0, sym.block
         token = torch.zeros(1, dtype=torch.int32, device="cuda")
@@ -284,13 +301,18 @@ def main():
 
     def build():
         if sym is not None:
-            issued[0] = float(sym.build_spectrum(phi[:R_tot], defer_join=R_tot < n))
-            launches[0] = sym.launches
+            cur = syms[step_no[0] % len(syms)]
+            pipelined = len(syms) == 2
+            issued[0] = float(cur.build_spectrum(phi[:R_tot], defer_join=pipelined or R_tot < n))
+            launches[0] = cur.launches
             if R_tot < n:  # the plain remainder runs under the last peer copies of the shared square
-                kd.gram_i8(phi[row0:row0 + R], phi[R_tot:], row_index0=row0, col_index0=R_tot, out_dtype=1, m_sub=0, out=out[:, R_tot:])
+                kd.gram_i8(phi[row0:row0 + R], phi[R_tot:], row_index0=row0, col_index0=R_tot, out_dtype=1, m_sub=0, out=cur.block[:, R_tot:])
                 issued[0] += float(R) * (n - R_tot)
                 launches[0] += 1
-                sym.join()
+                if not pipelined:
+                    cur.join()
+            if pipelined:
+                kd.sharded_mark(step_no[0] % 2)
         elif sym1:
             kd.gram_i8(phi[:R], phi[:R], out_dtype=1, symmetric=True, m_sub=0, out=out[:, :R])
             issued[0], launches[0] = sym_issued_entries(R), 1
@@ -313,11 +335,22 @@ def main():
         for lo, hi in phi_ranges:
             kd.spectrum_phi(planes[lo:hi], L, KS, out=phi[lo:hi])
 
+    def sync_before_step():
+        """What must have happened before this step may overwrite its buffers.  One buffer set: every rank's deliveries of
+        the previous step (each rank joined its copies at the end of its build).  Two sets: every rank's deliveries of the
+        step before the previous one -- this rank's stream waits for its own copies of that step, the all-reduce of a
+        token then orders the step after every rank's wait."""
+        if sym is None:
+            return
+        if len(syms) == 2:
+            kd.sharded_wait_mark(step_no[0] % 2)
+        dist.all_reduce(token)
+
     def step():
+        sync_before_step()
         build_phi()
         build()
-        if sym is not None:
-            dist.all_reduce(token)  # orders step k+1 after every rank's deliveries of step k
+        step_no[0] += 1
 
     def barrier():
         if dist is not None:
@@ -333,12 +366,17 @@ def main():
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2 * args.steps + 2)]
     ev[0].record()
     for i in range(args.steps):
+        sync_before_step()
         build_phi()
         ev[2 * i + 1].record()
         build()
         ev[2 * i + 2].record()
-        if sym is not None:
-            dist.all_reduce(token)
+        step_no[0] += 1
+    if sym is not None:  # the timed region ends when the last builds' deliveries are complete on every rank
+        if len(syms) == 2:
+            kd.sharded_wait_mark(0)
+            kd.sharded_wait_mark(1)
+        dist.all_reduce(token)
     ev[-1].record()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
@@ -356,6 +394,12 @@ def main():
     if sym is not None:
         sym.finish()
     parity = check_parity(torch, out, codes, row0, R, n, R_tot, rank, world)
+    if sym_b is not None:  # both buffer sets hold a complete Gram block-row
+        sym_b.finish()
+        pb = check_parity(torch, sym_b.block, codes, row0, R, n, R_tot, rank, world)
+        parity["ok"] = parity["ok"] and pb["ok"]
+        parity["tiles_per_rank"] += pb["tiles_per_rank"]
+        parity["entries_per_rank"] += pb["entries_per_rank"]
     parity["ok"] = bool(allmin_int(1 if parity["ok"] else 0))
     parity["ranks"] = world
     if not parity["ok"]:
@@ -410,6 +454,9 @@ def main():
             out = None
             sym.close()
             sym = None
+        if sym_b is not None:
+            sym_b.close()
+            sym_b = None
         del out
         torch.cuda.empty_cache()
         kernels = extras(kd, torch, dist, codes, planes, peaks, rank, world, allmax, allmin_int)
@@ -429,6 +476,8 @@ def main():
     if sym is not None:
         out = None
         sym.close()
+    if sym_b is not None:
+        sym_b.close()
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()

@@ -187,6 +187,11 @@ int kmg_gram_i8_dev(const int8_t* d_phi_rows, const int8_t* d_phi_cols, int64_t 
  * d_sd (nullable): sqrt(diag) of all n rows, fused cosine normalisation.  computed_entries (nullable out). */
 int kmg_gram_sharded_stage_bytes(int n_parts, const int64_t* part_row0, int part, int out_dtype, int64_t* bytes);
 int kmg_gram_sharded_join(void* stream);
+/* kmg_gram_sharded_mark(slot): remember "every peer copy enqueued so far" (slot 0..3, per host thread);
+ * kmg_gram_sharded_wait_mark(slot, stream): `stream` waits for exactly that point.  With two sets of block-row buffers the
+ * next build starts while the previous build's copies drain, and the build after it waits for the right copies only. */
+int kmg_gram_sharded_mark(int slot);
+int kmg_gram_sharded_wait_mark(int slot, void* stream);
 /* GEMM launches one call of kmg_gram_i8_sharded_dev enqueues for this part (host utility, no GPU) */
 int kmg_gram_sharded_launches(int n_parts, const int64_t* part_row0, int part, int exchange, int* launches);
 int kmg_gram_i8_sharded_dev(const int8_t* d_phi, int64_t n, int64_t width, int64_t ld_phi, int n_parts, int part,

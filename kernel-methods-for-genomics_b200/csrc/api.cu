@@ -775,6 +775,34 @@ int kmg_gram_sharded_join(void* stream) {
     return KMG_OK;
 }
 
+// Marks on the copy stream: kmg_gram_sharded_mark(slot) records "every peer copy enqueued so far" in one of four per-thread
+// events; kmg_gram_sharded_wait_mark(slot, stream) makes `stream` wait for that point only -- not for copies enqueued later.
+// With two sets of block-row buffers this lets build k+1 start while the copies of build k are still draining, and build
+// k+2 (same buffers as k) wait for exactly the copies of build k.
+namespace {
+thread_local cudaEvent_t g_marks[4] = {nullptr, nullptr, nullptr, nullptr};
+thread_local int g_marks_dev = -1;
+}
+int kmg_gram_sharded_mark(int slot) {
+    int rc = kmg_rt_require_device();
+    if (rc) return rc;
+    KMG_REQUIRE(slot >= 0 && slot < 4, KMG_ERR_ARG, "sharded_mark: slot 0..3");
+    cudaStream_t s0, copy;
+    if ((rc = kmg_rt_get_streams(&s0, &copy))) return rc;
+    int dev = 0;
+    KMG_CUDA_CHECK(cudaGetDevice(&dev));
+    if (g_marks_dev != dev) { for (int q = 0; q < 4; ++q) g_marks[q] = nullptr; g_marks_dev = dev; }
+    if (g_marks[slot] == nullptr) KMG_CUDA_CHECK(cudaEventCreateWithFlags(&g_marks[slot], cudaEventDisableTiming));
+    KMG_CUDA_CHECK(cudaEventRecord(g_marks[slot], copy));
+    return KMG_OK;
+}
+int kmg_gram_sharded_wait_mark(int slot, void* stream) {
+    KMG_REQUIRE(slot >= 0 && slot < 4, KMG_ERR_ARG, "sharded_wait_mark: slot 0..3");
+    if (g_marks[slot] == nullptr) return KMG_OK;  // never marked: nothing to wait for
+    KMG_CUDA_CHECK(cudaStreamWaitEvent((cudaStream_t)stream, g_marks[slot], 0));
+    return KMG_OK;
+}
+
 // Measured int8 tensor-core peak (mma_peak.cu): enqueue `iters` x 4 back-to-back MMAs per CTA pair; the caller times it.
 int kmg_mma_peak_i8_dev(int iters, int64_t* ops, void* stream) {
     int rc = kmg_rt_require_device();

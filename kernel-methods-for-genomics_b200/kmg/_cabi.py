@@ -68,6 +68,8 @@ PROTOTYPES = {
     "kmg_gram_i8_dev": (_i32, [_vp, _vp, _i64, _i64, _i64, _i64, _i64, _i64, _vp, _i64, _i32, _i32, _vp, _vp, _i32, _vp]),
     "kmg_gram_sharded_stage_bytes": (_i32, [_i32, _vp, _i32, _i32, _vp]),
     "kmg_gram_sharded_join": (_i32, [_vp]),
+    "kmg_gram_sharded_mark": (_i32, [_i32]),
+    "kmg_gram_sharded_wait_mark": (_i32, [_i32, _vp]),
     "kmg_gram_sharded_launches": (_i32, [_i32, _vp, _i32, _i32, _vp]),
     "kmg_gram_i8_sharded_dev": (_i32, [_vp, _i64, _i64, _i64, _i32, _i32, _vp, _vp, _i64, _i32, _vp, _i32, _vp, _vp, _vp]),
     "kmg_mma_peak_i8_dev": (_i32, [_i32, _vp, _vp]),

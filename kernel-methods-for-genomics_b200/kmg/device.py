@@ -114,6 +114,16 @@ def sharded_join():
     check(_cabi.lib().kmg_gram_sharded_join(_stream()))
 
 
+def sharded_mark(slot):
+    """Remember the peer copies enqueued so far (slot 0..3)."""
+    check(_cabi.lib().kmg_gram_sharded_mark(int(slot)))
+
+
+def sharded_wait_mark(slot):
+    """The current stream waits for the copies remembered in `slot` (and for nothing enqueued after them)."""
+    check(_cabi.lib().kmg_gram_sharded_wait_mark(int(slot), _stream()))
+
+
 def gram_i8_sharded(phi, part_row0, part, part_ptrs, ldo, out_dtype=KMG_OUT_F64, sd=None, stage=None, exchange=None, defer_join=False):
     """Part `part`'s launch of the sharded symmetric Gram of all rows of `phi` (kmg_gram_i8_sharded_dev).
     part_row0: len(parts)+1 boundaries; part_ptrs: device address (int) of every part's block-row buffer (row stride ldo
