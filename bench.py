@@ -435,6 +435,15 @@ def main():
         "entries_issued_per_s_per_gpu": issued[0] / (ms_per_step * 1e-3),
     }
 
+    # The block-row buffers (2 x 57 GB per GPU at N = 8) are checked and done with: give the memory back before the
+    # end-to-end leg and the per-kernel numbers allocate theirs.  close() synchronises and barriers, so no peer still
+    # writes into a buffer that is being unmapped.
+    out = None
+    for s_ in syms:
+        s_.close()
+    sym, sym_b, syms = None, None, []
+    torch.cuda.empty_cache()
+
     # ---- end to end through the reference-facing C-ABI with host buffers (kmg_spectrum_host)
     e2e = None
     if not args.no_e2e:
@@ -450,15 +459,6 @@ def main():
     }
 
     if not args.no_extras:
-        if sym is not None:
-            out = None
-            sym.close()
-            sym = None
-        if sym_b is not None:
-            sym_b.close()
-            sym_b = None
-        del out
-        torch.cuda.empty_cache()
         kernels = extras(kd, torch, dist, codes, planes, peaks, rank, world, allmax, allmin_int)
         line["kernels"] = kernels
     if rank == 0 and world == 1 and not args.no_e2e:
@@ -473,11 +473,6 @@ def main():
                                           "dense Phi + dot products as kernels.py:12-47, all host threads)"}
     if rank == 0:
         print(json.dumps(line), flush=True)
-    if sym is not None:
-        out = None
-        sym.close()
-    if sym_b is not None:
-        sym_b.close()
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
