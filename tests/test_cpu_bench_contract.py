@@ -29,3 +29,54 @@ def test_product_arm_needs_a_gpu():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1"], capture_output=True, text=True,
                          timeout=600, cwd=ROOT)
     assert out.returncode != 0 and "no CPU fallback" in (out.stderr + out.stdout)
+
+
+def _dryrun(world, extra=(), n="2048"):
+    """bench.py's main() with the device layer replaced by oracle-backed stand-ins (tests/bench_flow_dryrun.py)."""
+    script = os.path.join(ROOT, "tests", "bench_flow_dryrun.py")
+    flags = ["--gpus", str(world), "--steps", "2", "--no-extras", "--no-e2e", "--no-cpu", *extra]
+    if world == 1:
+        cmd = [sys.executable, script, *flags]
+    else:
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
+               "--master-port", str(29700 + world + (7 if extra else 0)), script, *flags]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT, env={**os.environ, "DRY_N": n, "DRY_ROWS": "512"})
+    assert out.returncode == 0, (out.stdout + out.stderr)[-3000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1, out.stdout[-2000:]  # rank 0 alone prints, one line
+    return json.loads(lines[0])
+
+
+def _check_line(d, world):
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype",
+                "data", "config", "e2e", "gpu_launches", "roofline", "clocks", "parity_checked", "exchange"):
+        assert key in d, key
+    assert d["metric"] == "gram_entries_per_sec" and d["unit"] == "entries/s" and d["n_gpus"] == world and d["warmup"] >= 3
+    assert d["scaling"] == "weak" and d["vs_baseline"] is None and d["higher_is_better"] is True and d["value"] > 0
+    r = d["roofline"]
+    assert r["bound"] == "tensor" and r["peak"] > 0 and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12 and "traffic" in r
+    assert d["parity_checked"] is True and d["parity"]["ranks"] == world and d["parity"]["bar"] == "bit-exact"
+    assert d["gpu_launches"] == (r["phi_launches_per_step"] + r["gemm_launches_per_step"]) * d["steps"] > 0
+    assert d["config"]["block_rows_built"] == world and "model" not in d["config"]
+
+
+def test_product_arm_control_flow_one_gpu():
+    d = _dryrun(1)
+    _check_line(d, 1)
+    assert d["roofline"]["gemm_launches_per_step"] == 2        # symmetric leading square + plain remainder
+    assert 0.5 < d["roofline"]["entries_issued_over_entries_held"] < 1.0
+    assert d["roofline"]["traffic"] is not None
+
+
+def test_product_arm_control_flow_two_ranks_two_buffer_sets():
+    d = _dryrun(2)
+    _check_line(d, 2)
+    assert d["exchange"] == {"mode": "staged", "buffers": 2}
+    assert d["parity"]["tiles_per_rank"] == 16                  # both buffer sets went through the oracle check
+    assert d["roofline"]["traffic"] is None                     # no ncu capture of a torchrun job
+
+
+def test_product_arm_control_flow_two_ranks_single_buffer_no_remainder():
+    d = _dryrun(2, extra=("--single-buffer",), n="1024")
+    _check_line(d, 2)
+    assert d["exchange"] == {"mode": "staged", "buffers": 1} and d["roofline"]["phi_rows_built_per_step"] == 1024
