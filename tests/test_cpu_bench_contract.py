@@ -80,3 +80,15 @@ def test_product_arm_control_flow_two_ranks_single_buffer_no_remainder():
     d = _dryrun(2, extra=("--single-buffer",), n="1024")
     _check_line(d, 2)
     assert d["exchange"] == {"mode": "staged", "buffers": 1} and d["roofline"]["phi_rows_built_per_step"] == 1024
+
+
+def test_reference_arm_under_torchrun_prints_on_rank_zero_only():
+    """N > 1: the driver launches the reference arm like the product arm; rank 0 alone runs and prints, the others exit 0."""
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                          "--master-port", "29741", os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1"],
+                         capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert out.returncode == 0, (out.stdout + out.stderr)[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["config"]["block_rows_built"] == 2 and d["value"] > 0
