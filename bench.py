@@ -471,6 +471,10 @@ def main():
         line["cpu_baseline"] = {"value": v, "unit": "entries/s", "cores": oc.num_threads(), "kind": "port",
                                 "sample": f"{rows} x {cols} entries of the block-row, 3 timed passes of {dtc:.1f} s (oracle/kmg_oracle.c: "
                                           "dense Phi + dot products as kernels.py:12-47, all host threads)"}
+        if "kernels" in line:  # the same CPU port on the other configs, next to their GPU numbers
+            for name, base in cpu_kernel_baselines(oc).items():
+                if name in line["kernels"]:
+                    line["kernels"][name]["cpu_baseline"] = base
     if rank == 0:
         print(json.dumps(line), flush=True)
     if dist is not None:
@@ -607,6 +611,34 @@ def e2e_leg(torch, kh, codes, row0, R, n, world, args, barrier, allmax):
             res["d2h_bytes_per_step"] = int(e2e_rows * n * 8)
     finally:
         kh.set_d2h_mode("widen")
+    return res
+
+
+def cpu_kernel_baselines(oc, budget_s=2.0):
+    """The oracle's plain-C restatement (all host threads) on a bounded sample of every other BASELINE config, entries/s:
+    the CPU side of the `kernels.*` entries (N = 1, rank 0; the reference itself is pure Python and cannot travel).
+    Each sample is sized from a small calibration call to about `budget_s` seconds."""
+    z = np.load(os.path.join(ROOT, "tests", "golden", "dna9000.npz"))
+    legs = {
+        "mismatch_k10_m1_n9000": (z["codes"], lambda r, c: oc.mismatch_raw_block(r, c, 10, 1), "mismatch_raw_block (k,m)=(10,1): W^2 window tests per entry, raw counts"),
+        "wd_d10_n100000": (synthetic_codes(4096, 4), lambda r, c: oc.wd_block(r, c, 10, row_index0=0, col_index0=8192), "wd_block d=10 (kernels.py:64-81 per pair)"),
+        "la_affine_n20000": (synthetic_codes(4096, 5), lambda r, c: oc.la_block(r, c, 11, 1, 0.5, 0, row_index0=0, col_index0=8192), "la_block affine e=11 d=1 beta=0.5 (10 201 DP cells per entry)"),
+    }
+    res = {}
+    for name, (codes, fn, what) in legs.items():
+        try:
+            t0 = time.perf_counter()
+            fn(codes[:8], codes[64:128])
+            rate = 8 * 64 / max(time.perf_counter() - t0, 1e-6)  # entries/s, pessimistic (thread start-up included)
+            cols = 512
+            rows = int(max(8, min(2048, budget_s * rate * 1.5 / cols)))
+            t0 = time.perf_counter()
+            fn(codes[:rows], codes[2048:2048 + cols])
+            dt = time.perf_counter() - t0
+            res[name] = {"value": rows * cols / dt, "unit": "entries/s", "cores": oc.num_threads(), "kind": "port",
+                         "sample": f"{rows} x {cols} entries in {dt:.2f} s, oracle/kmg_oracle.c {what}"}
+        except Exception as exc:  # noqa: BLE001 - a reported baseline must not cost the bench line
+            res[name] = {"value": None, "error": f"{type(exc).__name__}: {exc}"}
     return res
 
 

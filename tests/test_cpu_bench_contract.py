@@ -92,3 +92,16 @@ def test_reference_arm_under_torchrun_prints_on_rank_zero_only():
     assert len(lines) == 1
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["config"]["block_rows_built"] == 2 and d["value"] > 0
+
+
+def test_per_kernel_cpu_baselines():
+    """bench.py's CPU side of the kernels.* entries: bounded samples of the oracle's C port, one per BASELINE config."""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import bench
+    import oracle_c as oc
+    oc.build()
+    res = bench.cpu_kernel_baselines(oc, budget_s=0.2)
+    assert set(res) == {"mismatch_k10_m1_n9000", "wd_d10_n100000", "la_affine_n20000"}
+    for name, base in res.items():
+        assert base["value"] > 0 and base["kind"] == "port" and base["cores"] >= 1 and base["unit"] == "entries/s", (name, base)
