@@ -172,3 +172,48 @@ def test_solver_dropins_import_without_a_gpu():
     if not torch.cuda.is_available():
         with pytest.raises(_cabi.KmgError):
             m.fit(pd.DataFrame({"Id": [0, 1]}), pd.DataFrame({"Id": [0, 1], "Bound": [1.0, -1.0]}))
+
+
+def test_header_is_plain_c_and_a_c_program_links_the_library(tmp_path):
+    """The boundary is a C ABI: include/kmg.h compiles as strict C99 and as C++11, and a C program -- no Python, no torch --
+    links libkmg.so and calls host-side entry points (a compute entry point without a GPU reports an error, it does not
+    fall back to the CPU)."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("needs gcc")
+    inc = os.path.join(ROOT, "include")
+    libdir = os.path.join(ROOT, "kernel-methods-for-genomics_b200")
+    src = tmp_path / "t.c"
+    src.write_text(r'''
+#include <stdio.h>
+#include <stdint.h>
+#include "kmg.h"
+int main(void) {
+    int64_t T[11];
+    int ks[2] = {3, 6};
+    if (kmg_mismatch_table_host(10, 1, T) != 0) return 2;
+    printf("T0=%lld T1=%lld width=%d\n", (long long)T[0], (long long)T[1], (int)kmg_spectrum_phi_width(ks, 2));
+    {
+        unsigned char seqs[2 * 8] = {0,1,2,3,0,1,2,3, 3,2,1,0,3,2,1,0};
+        double K[4];
+        int k1[1] = {2};
+        int rc = kmg_spectrum_host(seqs, 2, NULL, 0, 8, 1, k1, 1, K, 2);
+        printf("rc=%d err=%s\n", rc, kmg_last_error());
+    }
+    return 0;
+}
+''')
+    for compiler, std, name in (("gcc", "-std=c99", "t.c"), ("g++", "-std=c++11", "t.cpp")):
+        if name == "t.cpp":
+            (tmp_path / name).write_text(src.read_text())
+        subprocess.check_call([compiler, std, "-Wall", "-Wextra", "-pedantic", "-Werror", f"-I{inc}", "-fsyntax-only", str(tmp_path / name)])
+    exe = tmp_path / "t"
+    subprocess.check_call(["gcc", "-std=c99", f"-I{inc}", str(src), "-o", str(exe), f"-L{libdir}", "-lkmg", f"-Wl,-rpath,{libdir}"])
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    first, second = out.stdout.strip().splitlines()
+    assert first == "T0=31 T1=4 width=4224", first          # (10,1): 1 + 3*10 neighbours; distance 1: the two k-mers + 2 letters; pad128(4^3 + 4^6)
+    import torch
+    if not torch.cuda.is_available():
+        assert second.startswith("rc=-") and "err=" in second and len(second) > len("rc=-1 err="), second
