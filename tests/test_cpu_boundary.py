@@ -198,7 +198,7 @@ int main(void) {
         unsigned char seqs[2 * 8] = {0,1,2,3,0,1,2,3, 3,2,1,0,3,2,1,0};
         double K[4];
         int k1[1] = {2};
-        int rc = kmg_spectrum_host(seqs, 2, NULL, 0, 8, 1, k1, 1, K, 2);
+        int rc = kmg_spectrum_host(seqs, 2, NULL, 0, 8, KMG_SEQ_CODES, k1, 1, K, 2);
         printf("rc=%d err=%s\n", rc, kmg_last_error());
     }
     return 0;
