@@ -158,3 +158,29 @@ class QuadForms:
             check(_lib().kmg_weighted_dot_dev(self._kt.ptr, self.n, g.ptr, g.cols, self._alpha.ptr, self.n,
                                               self._part.ptr, res_m, None))
         return -float(degree) * self._res.to_host()[0]
+
+
+def reformat_data(data, grams, ID):
+    """utils.reformat_data (utils.py:280-312) for Grams that live on the device: restrict every kernel to the rows of one
+    data set -- train, then validation, then test -- and renumber the Ids 0 .. n_sub-1 in that order.  `grams` are
+    DeviceGram objects over all sequences (Ids `ID` in kernel order); the sub-blocks K[idx][:, idx] are gathered on the
+    device (kmg_gather_dev) and stay there, so a 9 000^2 -> 3 000^2 restriction moves no matrix over PCIe.
+    data = (X_train, y_train, X_val, y_val, X_test), DataFrames with an 'Id' column; their 'Id' columns are rewritten in
+    place, as the reference does.  Returns (X_train, y_train, X_val, y_val, X_test, sub_grams, new_ID).
+    Host arrays are not accepted: for those the reference's own utils.reformat_data applies as it is."""
+    from ._dual import rows_of
+    X_train, y_train, X_val, y_val, X_test = data
+    for g in grams:
+        if not hasattr(g, "gather"):
+            raise TypeError("resident.reformat_data takes device-resident Grams (DeviceGram); use utils.reformat_data for numpy arrays")
+    parts = (X_train, X_val, X_test)
+    wanted = np.concatenate([p.loc[:, 'Id'].to_numpy() for p in parts])
+    idx = rows_of(ID, wanted)
+    sub = [g.gather(idx) for g in grams]
+    new_ID = np.arange(wanted.size)
+    cuts = np.cumsum([0] + [p.shape[0] for p in parts])
+    for p, lo, hi in zip(parts, cuts[:-1], cuts[1:]):
+        p.Id = new_ID[lo:hi]
+    y_train.Id = new_ID[:y_train.shape[0]]
+    y_val.Id = new_ID[cuts[1]:cuts[1] + y_val.shape[0]]
+    return X_train, y_train, X_val, y_val, X_test, sub, new_ID

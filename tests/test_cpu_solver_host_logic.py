@@ -113,3 +113,44 @@ def test_klr_stops_updating_once_the_step_is_below_tol(golden, gs, stand_ins):
     sub = np.ascontiguousarray(K[fit][:, fit])
     W, z = ref.IRLS(sub, y, np.zeros(fit.size))
     assert np.allclose(one.a, ref.WKRR(sub, W, z), rtol=1e-12, atol=0)
+
+
+def test_resident_reformat_data_follows_the_reference():
+    """kmg.resident.reformat_data against a literal restatement of utils.reformat_data (utils.py:296-312), with a numpy
+    stand-in for the device gather (DeviceGram.gather itself: tests/test_gpu_solvers.py)."""
+    from kmg import resident
+
+    class G:
+        def __init__(self, K):
+            self.K = K
+
+        def gather(self, idx):
+            return G(self.K[idx][:, idx])
+
+    rng = np.random.default_rng(3)
+    n = 40
+    ID = rng.permutation(np.arange(100, 100 + n))
+    kernels = [rng.standard_normal((n, n)) for _ in range(2)]
+    ids = rng.permutation(ID)[:24]
+
+    def frames():
+        Xtr, Xva, Xte = (pd.DataFrame({"Id": ids[a:b], "seq": ["A"] * (b - a)}) for a, b in ((0, 12), (12, 18), (18, 24)))
+        ytr = pd.DataFrame({"Id": ids[0:12], "Bound": np.ones(12)})
+        yva = pd.DataFrame({"Id": ids[12:18], "Bound": -np.ones(6)})
+        return Xtr, ytr, Xva, yva, Xte
+
+    # the reference, restated
+    Xtr, ytr, Xva, yva, Xte = frames()
+    ID_ = np.concatenate((np.array(Xtr.loc[:, 'Id']), np.array(Xva.loc[:, 'Id']), np.array(Xte.loc[:, 'Id'])))
+    idx = np.array([np.where(ID == ID_[i])[0] for i in range(len(ID_))]).squeeze()
+    want_k = [K[idx][:, idx] for K in kernels]
+
+    got = resident.reformat_data(frames(), [G(K) for K in kernels], ID)
+    gXtr, gytr, gXva, gyva, gXte, sub, new_ID = got
+    assert np.array_equal(new_ID, np.arange(24))
+    for g, w in zip(sub, want_k):
+        assert np.array_equal(g.K, w)
+    assert list(gXtr.Id) == list(range(0, 12)) and list(gXva.Id) == list(range(12, 18)) and list(gXte.Id) == list(range(18, 24))
+    assert list(gytr.Id) == list(range(0, 12)) and list(gyva.Id) == list(range(12, 18))
+    with pytest.raises(TypeError):
+        resident.reformat_data(frames(), kernels, ID)
